@@ -1,0 +1,742 @@
+"""
+oracle/gpsig_oracle.py -- float64 NumPy restatement of tgcsaba/GPSig's signature-kernel covariance path.
+
+THIS IS TEST INFRASTRUCTURE, NOT PRODUCT.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+`--impl reference` legs may import it.  The product (gpsig_b200/) never does and fails loudly without its CUDA library.
+
+Pinning status
+--------------
+* Pinned against the reference ITSELF: the unmodified sources under /root/reference/gpsig are executed in the build
+  container on a numpy-backed TensorFlow/GPflow stand-in (tools/refshim) by tests/golden/make_golden.py; their
+  outputs are committed as tests/golden/*.npz and tests/test_oracle_golden.py checks every function below against
+  them (signature_algs.*, SignatureKernel.K/Kdiag/K_tens/K_tens_vs_seq/K_tens_n_seq_covs/K_seq_n_seq_covs for all
+  static kernels, lags, Kuu/Kuf/Kuu_Kuf_Kff, and the low-rank algebra on injected draws).
+* Pinned against the property the reference's only check pins (notebooks/signature_kernel.ipynb:75-140,209-310):
+  order=M linear kernel == inner products of true truncated signatures; esig is replaced by `chen_signature` below.
+* PARITY UNPINNED: gpflow==1.5.1 arithmetic that is not in /root/reference (base_conditional, gauss_kl,
+  likelihood variational expectations -> the SVGP ELBO).  These follow GPflow 1.5.1's published formulas
+  (gpflow/conditionals.py, gpflow/kullback_leiblers.py, gpflow/likelihoods.py) and are cross-checked only by
+  self-consistency (dense Gaussian algebra) in tests/test_oracle_props.py.
+* TF's random streams cannot be reproduced without TF: low-rank parity is defined on injected draws.
+
+All `file:line` citations are relative to /root/reference/.
+"""
+import numpy as np
+
+JITTER = 1e-6  # gpflow 1.5.1 settings.numerics.jitter_level (used at kernels.py:431,463,578,656; models.py:65)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------------------------------
+def _excl_cumsum(a, axis):
+    """tf.cumsum(exclusive=True): [a,b,c] -> [0,a,a+b] (shift of the inclusive scan)."""
+    c = np.cumsum(a, axis=axis)
+    out = np.zeros_like(c)
+    src = [slice(None)] * a.ndim
+    dst = [slice(None)] * a.ndim
+    src[axis] = slice(0, -1)
+    dst[axis] = slice(1, None)
+    out[tuple(dst)] = c[tuple(src)]
+    return out
+
+
+def _diff2d(M):
+    """signature_algs.py:26 -- 2-D increment over the two time axes (axis 1 and the last axis)."""
+    return M[:, 1:, ..., 1:] + M[:, :-1, ..., :-1] - M[:, :-1, ..., 1:] - M[:, 1:, ..., :-1]
+
+
+def _level0(M):
+    if M.ndim == 4:
+        return np.ones((M.shape[0], M.shape[2]))
+    return np.ones((M.shape[0],))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# gpsig/signature_algs.py
+# ----------------------------------------------------------------------------------------------------------------
+def signature_kern_first_order(M, num_levels, difference=True):
+    """signature_algs.py:8-35.  M: (n1,L1,n2,L2) or (n,L,L) -> (num_levels+1,n1,n2) or (num_levels+1,n)."""
+    M = np.asarray(M, dtype=np.float64)
+    K = [_level0(M)]
+    if difference:
+        M = _diff2d(M)
+    K.append(M.sum(axis=(1, -1)))
+    R = M
+    for _ in range(2, num_levels + 1):
+        R = M * _excl_cumsum(_excl_cumsum(R, 1), -1)
+        K.append(R.sum(axis=(1, -1)))
+    return np.stack(K, axis=0)
+
+
+def signature_kern_higher_order(M, num_levels, order=2, difference=True):
+    """signature_algs.py:37-74.  Grid R[a][b] of size d x d, d=min(level,order)."""
+    M = np.asarray(M, dtype=np.float64)
+    K = [_level0(M)]
+    if difference:
+        M = _diff2d(M)
+    K.append(M.sum(axis=(1, -1)))
+    R = [[M]]
+    for i in range(2, num_levels + 1):
+        d = min(i, order)
+        dp = len(R)
+        Rn = [[None] * d for _ in range(d)]
+        total = sum(R[a][b] for a in range(dp) for b in range(dp))
+        Rn[0][0] = M * _excl_cumsum(_excl_cumsum(total, 1), -1)
+        for j in range(2, d + 1):
+            col = sum(R[a][j - 2] for a in range(dp))        # R[:, j-2]  (:66)
+            row = sum(R[j - 2][b] for b in range(dp))        # R[j-2, :]  (:67)
+            Rn[0][j - 1] = (1.0 / j) * M * _excl_cumsum(col, 1)
+            Rn[j - 1][0] = (1.0 / j) * M * _excl_cumsum(row, -1)
+            for k in range(2, d + 1):
+                Rn[j - 1][k - 1] = (1.0 / (j * k)) * M * R[j - 2][k - 2]
+        K.append(sum(Rn[a][b] for a in range(d) for b in range(d)).sum(axis=(1, -1)))
+        R = Rn
+    return np.stack(K, axis=0)
+
+
+def tensor_kern(M, num_levels):
+    """signature_algs.py:76-99.  M: (T,nz,nz2) component Grams -> (num_levels+1,nz,nz2)."""
+    M = np.asarray(M, dtype=np.float64)
+    K = [np.ones(M.shape[1:])]
+    k = 0
+    for i in range(1, num_levels + 1):
+        R = M[k]
+        k += 1
+        for _ in range(1, i):
+            R = M[k] * R
+            k += 1
+        K.append(R)
+    return np.stack(K, axis=0)
+
+
+def signature_kern_tens_vs_seq_first_order(M, num_levels, difference=True):
+    """signature_algs.py:101-127.  M: (T,nz,n,L) -> (num_levels+1,nz,n)."""
+    M = np.asarray(M, dtype=np.float64)
+    if difference:
+        M = M[..., 1:] - M[..., :-1]
+    K = [np.ones(M.shape[1:3])]
+    k = 0
+    for i in range(1, num_levels + 1):
+        R = M[k]
+        k += 1
+        for _ in range(1, i):
+            R = M[k] * _excl_cumsum(R, 2)
+            k += 1
+        K.append(R.sum(axis=2))
+    return np.stack(K, axis=0)
+
+
+def signature_kern_tens_vs_seq_higher_order(M, num_levels, order=2, difference=True):
+    """signature_algs.py:129-160."""
+    M = np.asarray(M, dtype=np.float64)
+    if difference:
+        M = M[..., 1:] - M[..., :-1]
+    K = [np.ones(M.shape[1:3])]
+    k = 0
+    for i in range(1, num_levels + 1):
+        R = [M[k]]
+        k += 1
+        for j in range(1, i):
+            d = min(j + 1, order)
+            Rn = [M[k] * _excl_cumsum(sum(R), 2)]
+            for l in range(1, d):
+                Rn.append(1.0 / (l + 1) * M[k] * R[l - 1])
+            R = Rn
+            k += 1
+        K.append(sum(R).sum(axis=2))
+    return np.stack(K, axis=0)
+
+
+# ---- low-rank algebra (randomness injected) ---------------------------------------------------------------------
+def lr_pair_index(k1, k2):
+    """low_rank_calculations.py:165-170: row r of the k1*k2 outer product pairs A[..., r % k1] with B[..., r // k1]."""
+    r = np.arange(k1 * k2)
+    return r % k1, r // k1
+
+
+def sparse_scale(D, sparsity):
+    """low_rank_calculations.py:175-178."""
+    D = float(D)
+    return D / np.log(D) if sparsity == "log" else np.sqrt(D)
+
+
+def lr_hadamard_prod_sparse(A, B, R, s):
+    """low_rank_calculations.py:152-193 with the sparse Gaussian matrix R (k1*k2, r) given."""
+    A, B, R = (np.asarray(v, dtype=np.float64) for v in (A, B, R))
+    k1, k2 = A.shape[-1], B.shape[-1]
+    r = R.shape[1]
+    ia, ib = lr_pair_index(k1, k2)
+    nz = np.count_nonzero(R, axis=1) > 0
+    C = A.reshape(-1, k1)[:, ia[nz]] * B.reshape(-1, k2)[:, ib[nz]]
+    C = C @ R[nz]
+    return np.sqrt(s / r) * C.reshape(A.shape[:-1] + (r,))
+
+
+def lr_hadamard_prod_subsample(A, B, select, signs):
+    """low_rank_calculations.py:104-127 with the selected (a,b) index pairs and Rademacher signs given."""
+    A, B = np.asarray(A, dtype=np.float64), np.asarray(B, dtype=np.float64)
+    return A[..., select[:, 0]] * B[..., select[:, 1]] * np.asarray(signs, dtype=np.float64)
+
+
+def nystrom_map(X, kern, samples, diag_draw, jitter=JITTER):
+    """low_rank_calculations.py:26-61 with landmark rows `samples` and the U[0,1) diagonal draw given (Q8)."""
+    W = kern(samples, samples) + np.diag(jitter * np.asarray(diag_draw, dtype=np.float64))
+    S, U = np.linalg.eigh(W)
+    D = np.sqrt(S + jitter)
+    return (kern(X, samples) @ U) / D[None, :]
+
+
+def signature_kern_first_order_lr_feature(U, num_levels, projector, difference=True, literal=True):
+    """
+    signature_algs.py:162-192.  `projector(level_index, A, B)` stands for lr_hadamard_prod_rand(U, P, ...) with its
+    draws fixed.  literal=True reproduces quirk Q1 (:191 appends reduce_sum(U) -- every level >= 2 equals level 1);
+    literal=False appends reduce_sum(P), the evidently intended feature.
+    """
+    U = np.asarray(U, dtype=np.float64)
+    Phi = [np.ones((U.shape[0], 1))]
+    if difference:
+        U = U[:, 1:, :] - U[:, :-1, :]
+    Phi.append(U.sum(axis=1))
+    P = U
+    for i in range(2, num_levels + 1):
+        P = _excl_cumsum(P, 1)
+        P = projector(i - 2, U, P)
+        Phi.append(U.sum(axis=1) if literal else P.sum(axis=1))
+    return Phi
+
+
+def tensor_kern_lr_feature(U, num_levels, projector):
+    """signature_algs.py:194-222; projector(j-1, U[k], R) mirrors the seeds[j-1] indexing at :219."""
+    U = np.asarray(U, dtype=np.float64)
+    Phi = [np.ones((U.shape[1], 1))]
+    k = 0
+    for i in range(1, num_levels + 1):
+        R = U[k]
+        k += 1
+        for j in range(1, i):
+            R = projector(j - 1, U[k], R)
+            k += 1
+        Phi.append(R)
+    return Phi
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# static (state-space) kernels -- gpsig/kernels.py:765-993
+# ----------------------------------------------------------------------------------------------------------------
+def _inner(X, X2):
+    X2 = X if X2 is None else X2
+    return np.matmul(X, np.swapaxes(X2, -1, -2))
+
+
+def square_dist(X, X2=None):
+    """kernels.py:765-776: -2 X X2^T + |X|^2 + |X2|^2 (the expanded form, cancellation included)."""
+    Xs = np.sum(np.square(X), axis=-1)
+    X2s = Xs if X2 is None else np.sum(np.square(X2), axis=-1)
+    return -2.0 * _inner(X, X2) + Xs[..., :, None] + X2s[..., None, :]
+
+
+def euclid_dist(X, X2=None):
+    """kernels.py:779-781."""
+    return np.sqrt(np.maximum(square_dist(X, X2), 1e-40))
+
+
+def static_kernel(kind, X, X2=None, **p):
+    """All `_base_kern`s of kernels.py:786-993 (inputs are already lengthscale-scaled, kernels.py:358)."""
+    if kind == "linear":                                        # :799-806
+        return _inner(X, X2)
+    if kind == "cosine":                                        # :820-828
+        n1 = np.sqrt(np.sum(np.square(X), axis=-1))
+        n2 = n1 if X2 is None else np.sqrt(np.sum(np.square(X2), axis=-1))
+        return _inner(X, X2) / (n1[..., :, None] * n2[..., None, :])
+    if kind == "poly":                                          # :844-848
+        return (_inner(X, X2) + p.get("gamma", 1.0)) ** p.get("degree", 3.0)
+    if kind == "rbf":                                           # :862-864
+        return np.exp(-square_dist(X, X2) / 2)
+    if kind == "mix":                                           # :881-892
+        inner = _inner(X, X2)
+        Xs = np.sum(np.square(X), axis=-1)
+        X2s = Xs if X2 is None else np.sum(np.square(X2), axis=-1)
+        ds = Xs[..., :, None] + X2s[..., None, :] - 2 * inner
+        mixing = p.get("mixing", 0.5)
+        return mixing * np.exp(-ds / 2) + (1.0 - mixing) * inner
+    if kind == "matern12":                                      # :955-958
+        return np.exp(-euclid_dist(X, X2))
+    if kind == "matern32":                                      # :974-977
+        r = euclid_dist(X, X2)
+        return (1.0 + np.sqrt(3.0) * r) * np.exp(-np.sqrt(3.0) * r)
+    if kind == "matern52":                                      # :991-993
+        r = euclid_dist(X, X2)
+        return (1.0 + np.sqrt(5.0) * r + 5.0 / 3.0 * np.square(r)) * np.exp(-np.sqrt(5.0) * r)
+    if kind == "spectral":                                      # :921-942 ('exp' / 'rbf' families; 'mixed' is Q6)
+        X2 = X if X2 is None else X2
+        diff = X[None, :, None, :] - X2[None, None, :, :]
+        g, om, al = p["gamma"], p["omega"], p["alpha"]
+        sq = np.sum(np.square(diff * g[:, None, None, :]), axis=-1)
+        term = np.exp(-np.sqrt(sq) / 2) if p.get("family", "rbf") == "exp" else np.exp(-sq / 2)
+        spec = np.cos(2.0 * np.pi * np.sum(diff * om[:, None, None, :], axis=-1))
+        return np.sum(term * spec * al[:, None, None], axis=0)
+    raise ValueError("unknown static kernel %r" % kind)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# gpsig/lags.py
+# ----------------------------------------------------------------------------------------------------------------
+def add_lags_to_sequences(X, lags, jitter=JITTER):
+    """lags.py:7-63.  X (n,L,d), lags (P,) -> (n,L,P+1,d): linear interpolation at max(t-lag,0), t=l/(L-1)."""
+    X = np.asarray(X, dtype=np.float64)
+    lags = np.asarray(lags, dtype=np.float64)
+    L = X.shape[1]
+    time = np.arange(L, dtype=np.float64) / float(L - 1)
+    tq = np.maximum(time[:, None] - lags[None, :], 0.0)                     # (L,P)
+    dist = time[:, None, None] - tq[None, :, :]                             # (L,L,P)
+    left = np.argmax(np.where(dist > jitter, -np.inf, dist), axis=0)        # (L,P)  lags.py:23
+    right = left + 1
+    Xl, Xr = X[:, left, :], X[:, right, :]                                  # (n,L,P,d)
+    tl, tr = time[left], time[right]
+    Xq = Xl + (tq[None, ..., None] - tl[None, ..., None]) * (Xr - Xl) / (tr[None, ..., None] - tl[None, ..., None])
+    return np.concatenate((X[:, :, None, :], Xq), axis=2)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# gpsig/kernels.py -- SignatureKernel
+# ----------------------------------------------------------------------------------------------------------------
+class SignatureKernelOracle:
+    """
+    Mirrors SignatureKernel (kernels.py:15-761): same kwargs (`:18-19`), same 2-D (N, L*d) input convention
+    (`:417-419`), same normalisation / jitter placement, same level weighting.  `kind` picks the static kernel.
+    Parameters are held in constrained space (the value the reference reads inside @params_as_tensors).
+    """
+
+    def __init__(self, kind, input_dim, num_features, num_levels, active_dims=None, variances=1, lengthscales=1,
+                 order=1, normalization=True, difference=True, num_lags=None, low_rank=False, sigma=1.0,
+                 lags=None, lag_gamma=None, jitter=JITTER, **static_params):
+        if input_dim % num_features != 0:                                              # :98-101
+            raise ValueError("The arguments num_features and input_dim are not consistent.")
+        self.kind, self.input_dim, self.num_features, self.num_levels = kind, input_dim, num_features, num_levels
+        self.active_dims = active_dims
+        self.len_examples = input_dim // num_features
+        self.order = num_levels if (order <= 0 or order >= num_levels) else order     # :57  (Q9)
+        if self.order != 1 and low_rank:                                              # :59-60
+            raise NotImplementedError("Higher-order algorithms not compatible with low-rank mode (yet).")
+        self.normalization, self.difference, self.low_rank = normalization, difference, low_rank
+        self.variances = variances * np.ones(num_levels + 1)
+        self.sigma = float(sigma)
+        if num_lags is None:
+            self.num_lags = 0
+        else:
+            if not isinstance(num_lags, int) or num_lags < 0:                         # :74-75
+                raise ValueError("The variable num_lags most be a nonnegative integer or None.")
+            self.num_lags = num_lags
+        if self.num_lags > 0:                                                         # :78-82
+            self.lags = 0.1 * np.arange(1, self.num_lags + 1) if lags is None else np.asarray(lags, dtype=np.float64)
+            g = 1.0 / np.arange(1, self.num_lags + 2)
+            self.gamma = g / g.sum() if lag_gamma is None else np.asarray(lag_gamma, dtype=np.float64)
+        self.lengthscales = None if lengthscales is None else lengthscales * np.ones(num_features)
+        self.jitter = jitter
+        self.static_params = static_params
+
+    # -- pieces ------------------------------------------------------------------------------------------------
+    def _slice(self, X):
+        if X is None or self.active_dims is None:
+            return X
+        return X[..., self.active_dims]
+
+    def _base(self, X, X2=None):
+        return static_kernel(self.kind, X, X2, **self.static_params)
+
+    def _scale_seq(self, X):
+        """kernels.py:342-364."""
+        n, L, _ = X.shape
+        if self.num_lags > 0:
+            X = add_lags_to_sequences(X, self.lags)
+        X = X.reshape(n, L, self.num_lags + 1, self.num_features)
+        if self.lengthscales is not None:
+            X = X / self.lengthscales[None, None, None, :]
+        if self.num_lags > 0:
+            X = X * self.gamma[None, None, :, None]
+        return X.reshape(n, L, self.num_features * (self.num_lags + 1))
+
+    def _scale_tens(self, Z, increments):
+        """kernels.py:366-398."""
+        Z = np.asarray(Z, dtype=np.float64)
+        if self.lengthscales is None:
+            return Z
+        shp = Z.shape
+        Zr = Z.reshape(shp[:-1] + (self.num_lags + 1, self.num_features)) / self.lengthscales
+        if self.num_lags > 0:
+            Zr = Zr * self.gamma[:, None]
+        return Zr.reshape(shp)
+
+    def _recursion(self, M):
+        if self.order == 1:
+            return signature_kern_first_order(M, self.num_levels, difference=self.difference)
+        return signature_kern_higher_order(M, self.num_levels, order=self.order, difference=self.difference)
+
+    def _K_seq_diag(self, X):
+        """kernels.py:188-205: batched (n,L,L) Gram, same recursion on the 3-D tensor."""
+        return self._recursion(self._base(X))
+
+    def _K_seq(self, X, X2=None, row_block=None):
+        """kernels.py:208-237.  row_block only bounds memory (CPU baseline at large N); arithmetic is unchanged."""
+        n, L, d = X.shape
+        Y = X if X2 is None else X2
+        n2, L2 = Y.shape[0], Y.shape[1]
+        rb = n if row_block is None else row_block
+        out = []
+        for i0 in range(0, n, rb):
+            Xi = X[i0:i0 + rb]
+            M = self._base(Xi.reshape(-1, d), Y.reshape(-1, d)).reshape(Xi.shape[0], L, n2, L2)
+            out.append(self._recursion(M))
+        return np.concatenate(out, axis=1)
+
+    def _K_tens(self, Z, increments=False):
+        """kernels.py:263-283."""
+        T, nz, d = Z.shape[0], Z.shape[1], Z.shape[-1]
+        if increments:
+            M = self._base(Z.reshape(T, 2 * nz, d)).reshape(T, nz, 2, nz, 2)
+            M = M[:, :, 1, :, 1] + M[:, :, 0, :, 0] - M[:, :, 1, :, 0] - M[:, :, 0, :, 1]
+        else:
+            M = self._base(Z)
+        return tensor_kern(M, self.num_levels)
+
+    def _K_tens_vs_seq(self, Z, X, increments=False):
+        """kernels.py:313-340."""
+        T, nz, d = Z.shape[0], Z.shape[1], Z.shape[-1]
+        n, L = X.shape[0], X.shape[1]
+        Xf = X.reshape(n * L, d)
+        if increments:
+            M = self._base(Z.reshape(2 * nz * T, d), Xf).reshape(T, nz, 2, n, L)
+            M = M[:, :, 1] - M[:, :, 0]
+        else:
+            M = self._base(Z.reshape(nz * T, d), Xf).reshape(T, nz, n, L)
+        if self.order == 1:
+            return signature_kern_tens_vs_seq_first_order(M, self.num_levels, difference=self.difference)
+        return signature_kern_tens_vs_seq_higher_order(M, self.num_levels, order=self.order,
+                                                       difference=self.difference)
+
+    def _weights(self):
+        return self.sigma * self.variances
+
+    def _seqs(self, X, presliced=False):
+        X = np.asarray(X, dtype=np.float64)
+        if not presliced:
+            X = self._slice(X)
+        return X.reshape(X.shape[0], -1, self.num_features)
+
+    # -- public (kernels.py:400-761) ---------------------------------------------------------------------------
+    def K(self, X, X2=None, presliced=False, return_levels=False, presliced_X=False, presliced_X2=False,
+          row_block=None):
+        """kernels.py:400-476."""
+        if presliced:
+            presliced_X = presliced_X2 = True
+        X = self._seqs(X, presliced_X)
+        Xs = self._scale_seq(X)
+        if X2 is None:
+            K = self._K_seq(Xs, row_block=row_block)
+            if self.normalization:                                                    # :430-433  (Q7)
+                K = K + self.jitter * np.eye(X.shape[0])[None]
+                dsq = np.sqrt(np.diagonal(K, axis1=-2, axis2=-1))
+                K = K / (dsq[:, :, None] * dsq[:, None, :])
+        else:
+            X2 = self._seqs(X2, presliced_X2)
+            X2s = self._scale_seq(X2)
+            K = self._K_seq(Xs, X2s, row_block=row_block)
+            if self.normalization:                                                    # :455-469
+                d1 = np.sqrt(self._K_seq_diag(Xs) + self.jitter)
+                d2 = np.sqrt(self._K_seq_diag(X2s) + self.jitter)
+                K = K / (d1[:, :, None] * d2[:, None, :])
+        K = K * self._weights()[:, None, None]                                        # :471
+        return K if return_levels else K.sum(axis=0)
+
+    def Kdiag(self, X, presliced=False, return_levels=False):
+        """kernels.py:478-510."""
+        n = np.asarray(X).shape[0]
+        if self.normalization:
+            if return_levels:
+                return np.tile(self._weights()[:, None], [1, n])
+            return np.full((n,), self.sigma * np.sum(self.variances))
+        Xs = self._scale_seq(self._seqs(X, presliced))
+        Kd = self._K_seq_diag(Xs) * self._weights()[:, None]
+        return Kd if return_levels else Kd.sum(axis=0)
+
+    def K_tens(self, Z, return_levels=False, increments=False):
+        """kernels.py:512-536 (no normalisation of tensors)."""
+        K = self._K_tens(self._scale_tens(Z, increments), increments) * self._weights()[:, None, None]
+        return K if return_levels else K.sum(axis=0)
+
+    def K_tens_vs_seq(self, Z, X, return_levels=False, increments=False, presliced=False):
+        """kernels.py:538-588."""
+        Xs = self._scale_seq(self._seqs(X, presliced))
+        K = self._K_tens_vs_seq(self._scale_tens(Z, increments), Xs, increments)
+        if self.normalization:                                                        # :572-581
+            K = K / np.sqrt(self._K_seq_diag(Xs) + self.jitter)[:, None, :]
+        K = K * self._weights()[:, None, None]
+        return K if return_levels else K.sum(axis=0)
+
+    def K_tens_n_seq_covs(self, Z, X, full_X_cov=False, return_levels=False, increments=False, presliced=False):
+        """kernels.py:590-671."""
+        Xs = self._scale_seq(self._seqs(X, presliced))
+        Zs = self._scale_tens(Z, increments)
+        w = self._weights()
+        Kzz = self._K_tens(Zs, increments)
+        Kzx = self._K_tens_vs_seq(Zs, Xs, increments)
+        if full_X_cov:
+            Kxx = self._K_seq(Xs)
+            if self.normalization:                                                    # :632-638
+                Kxx = Kxx + self.jitter * np.eye(Xs.shape[0])[None]
+                dsq = np.sqrt(np.diagonal(Kxx, axis1=-2, axis2=-1))
+                Kxx = Kxx / (dsq[:, :, None] * dsq[:, None, :])
+                Kzx = Kzx / dsq[:, None, :]
+            Kxx = Kxx * w[:, None, None]
+        else:
+            Kxx = self._K_seq_diag(Xs)
+            if self.normalization:                                                    # :655-661
+                Kzx = Kzx / np.sqrt(Kxx + self.jitter)[:, None, :]
+                Kxx = np.tile(w[:, None], [1, Xs.shape[0]])
+            else:
+                Kxx = Kxx * w[:, None]
+        Kzz = Kzz * w[:, None, None]
+        Kzx = Kzx * w[:, None, None]
+        if return_levels:
+            return Kzz, Kzx, Kxx
+        return Kzz.sum(axis=0), Kzx.sum(axis=0), Kxx.sum(axis=0)
+
+    def K_seq_n_seq_covs(self, X, X2, full_X2_cov=False, return_levels=False, presliced=False, literal=True):
+        """
+        kernels.py:673-761 (InducingSequences).  X is never sliced (:679-680).  literal=True reproduces Q4 (the
+        normalised diag branch divides Kxx2 by sqrt(diag Kxx) twice, :713 then :750); literal=False divides once.
+        full_X2_cov=True with normalisation raises NameError in the reference (Q2); here the evident intent is
+        implemented and the test-suite marks it as unpinned.
+        """
+        X = np.asarray(X, dtype=np.float64)
+        X = X.reshape(X.shape[0], -1, self.num_features)
+        X2 = self._seqs(X2, presliced)
+        Xs, X2s = self._scale_seq(X), self._scale_seq(X2)
+        w = self._weights()
+        Kxx = self._K_seq(Xs)
+        Kxx2 = self._K_seq(Xs, X2s)
+        if self.normalization:                                                        # :707-713
+            Kxx = Kxx + self.jitter * np.eye(Xs.shape[0])[None]
+            dsq = np.sqrt(np.diagonal(Kxx, axis1=-2, axis2=-1))
+            Kxx = Kxx / (dsq[:, :, None] * dsq[:, None, :])
+            Kxx2 = Kxx2 / dsq[:, :, None]
+        if full_X2_cov:
+            K22 = self._K_seq(X2s)
+            if self.normalization:
+                K22 = K22 + self.jitter * np.eye(X2s.shape[0])[None]
+                d2 = np.sqrt(np.diagonal(K22, axis1=-2, axis2=-1))
+                Kxx2 = Kxx2 / d2[:, None, :]
+                K22 = K22 / (d2[:, :, None] * d2[:, None, :])
+            K22 = K22 * w[:, None, None]
+        else:
+            K22 = self._K_seq_diag(X2s)
+            if self.normalization:                                                    # :745-751
+                d2 = np.sqrt(K22 + self.jitter)
+                if literal:
+                    Kxx2 = Kxx2 / (dsq[:, :, None] * d2[:, None, :])
+                else:
+                    Kxx2 = Kxx2 / d2[:, None, :]
+                K22 = np.tile(w[:, None], [1, X2s.shape[0]])
+            else:
+                K22 = K22 * w[:, None]
+        Kxx = Kxx * w[:, None, None]
+        Kxx2 = Kxx2 * w[:, None, None]
+        if return_levels:
+            return Kxx, Kxx2, K22
+        return Kxx.sum(axis=0), Kxx2.sum(axis=0), K22.sum(axis=0)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# gpsig/inducing_variables.py
+# ----------------------------------------------------------------------------------------------------------------
+def _mix_zz(K, W):
+    """inducing_variables.py:56,83: K[0] + sum_m W_m K_m W_m^T."""
+    return K[0] + np.sum(np.matmul(np.matmul(W, K[1:]), np.swapaxes(W, -1, -2)), axis=0)
+
+
+def _mix_zx(K, W):
+    """inducing_variables.py:57,73."""
+    return K[0] + np.sum(np.matmul(W, K[1:]), axis=0)
+
+
+def Kuu(kern, Z, increments=False, jitter=0.0, W=None, sequences=False):
+    """inducing_variables.py:78-87 (tensors) / :101-110 (sequences)."""
+    if sequences:
+        K = kern.K(Z, presliced=True, return_levels=W is not None)
+    else:
+        K = kern.K_tens(Z, return_levels=W is not None, increments=increments)
+    if W is not None:
+        K = _mix_zz(K, W)
+    return K + jitter * np.eye(K.shape[-1])
+
+
+def Kuf(kern, Z, X, increments=False, W=None, sequences=False):
+    """inducing_variables.py:68-76 / :112-120."""
+    if sequences:
+        K = kern.K(Z, X, presliced_X=True, return_levels=W is not None)
+    else:
+        K = kern.K_tens_vs_seq(Z, X, return_levels=W is not None, increments=increments)
+    return _mix_zx(K, W) if W is not None else K
+
+
+def Kuu_Kuf_Kff(kern, Z, X, increments=False, jitter=0.0, full_f_cov=False, W=None, sequences=False, literal=True):
+    """inducing_variables.py:51-66 / :122-137.  full_f_cov=True raises NameError in the reference (Q5); the evident
+    intent (jitter*I on Kxx) is implemented."""
+    lv = W is not None
+    if sequences:
+        Kzz, Kzx, Kxx = kern.K_seq_n_seq_covs(Z, X, full_X2_cov=full_f_cov, return_levels=lv, literal=literal)
+    else:
+        Kzz, Kzx, Kxx = kern.K_tens_n_seq_covs(Z, X, full_X_cov=full_f_cov, return_levels=lv, increments=increments)
+    if lv:
+        Kzz, Kzx, Kxx = _mix_zz(Kzz, W), _mix_zx(Kzx, W), Kxx.sum(axis=0)
+    Kzz = Kzz + jitter * np.eye(Kzz.shape[-1])
+    Kxx = Kxx + (jitter * np.eye(Kxx.shape[-1]) if full_f_cov else jitter)
+    return Kzz, Kzx, Kxx
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# gpflow==1.5.1 pieces used by gpsig/models.py (NOT in /root/reference -> parity unpinned, published formulas)
+# ----------------------------------------------------------------------------------------------------------------
+def _tri_solve(L, B, lower=True, trans=False):
+    import scipy.linalg as sla
+    return sla.solve_triangular(L, B, lower=lower, trans="T" if trans else "N")
+
+
+def base_conditional(Kmn, Kmm, Knn, f, full_cov=False, q_sqrt=None, white=False):
+    """gpflow/conditionals.py (1.5.1) base_conditional; called at models.py:66.  f (Z,R), q_sqrt (R,Z,Z) or (Z,R)."""
+    R = f.shape[1]
+    Lm = np.linalg.cholesky(Kmm)
+    A = _tri_solve(Lm, Kmn)
+    if full_cov:
+        fvar = np.tile((Knn - A.T @ A)[None], [R, 1, 1])
+    else:
+        fvar = np.tile((Knn - np.sum(np.square(A), 0))[None], [R, 1])
+    if not white:
+        A = _tri_solve(Lm, A, trans=True)
+    fmean = A.T @ f
+    if q_sqrt is not None:
+        if q_sqrt.ndim == 2:
+            LTA = A * q_sqrt.T[:, :, None]
+        else:
+            LTA = np.matmul(np.swapaxes(np.tril(q_sqrt), -1, -2), A[None])
+        if full_cov:
+            fvar = fvar + np.matmul(np.swapaxes(LTA, -1, -2), LTA)
+        else:
+            fvar = fvar + np.sum(np.square(LTA), 1)
+    if not full_cov:
+        fvar = fvar.T
+    return fmean, fvar
+
+
+def gauss_kl(q_mu, q_sqrt, K=None):
+    """gpflow/kullback_leiblers.py (1.5.1) gauss_kl; called at models.py:49,52.  q_mu (Z,R), q_sqrt (R,Z,Z)|(Z,R)."""
+    Zn, R = q_mu.shape
+    white = K is None
+    if white:
+        alpha = q_mu
+    else:
+        Lp = np.linalg.cholesky(K)
+        alpha = _tri_solve(Lp, q_mu)
+    if q_sqrt.ndim == 2:
+        Lq_diag = q_sqrt
+        Lq_full = np.stack([np.diag(q_sqrt[:, r]) for r in range(R)])
+    else:
+        Lq_full = np.tril(q_sqrt)
+        Lq_diag = np.diagonal(Lq_full, axis1=-2, axis2=-1)
+    twoKL = np.sum(np.square(alpha)) - R * Zn - np.sum(np.log(np.square(Lq_diag)))
+    if white:
+        twoKL += np.sum(np.square(Lq_full if q_sqrt.ndim == 3 else q_sqrt))
+    else:
+        twoKL += sum(np.sum(np.square(_tri_solve(Lp, Lq_full[r]))) for r in range(R))
+        twoKL += R * np.sum(np.log(np.square(np.diag(Lp))))
+    return 0.5 * twoKL
+
+
+def gaussian_variational_expectations(Fmu, Fvar, Y, variance):
+    """gpflow/likelihoods.py Gaussian.variational_expectations."""
+    return -0.5 * np.log(2 * np.pi) - 0.5 * np.log(variance) - 0.5 * (np.square(Y - Fmu) + Fvar) / variance
+
+
+def bernoulli_variational_expectations(Fmu, Fvar, Y, num_gauss_hermite_points=20):
+    """gpflow/likelihoods.py Bernoulli (probit link with 1e-3 jitter) via Gauss-Hermite quadrature (ndiagquad)."""
+    from scipy.special import erf
+    gh_x, gh_w = np.polynomial.hermite.hermgauss(num_gauss_hermite_points)
+    gh_w = gh_w / np.sqrt(np.pi)
+    X = Fmu[..., None] + np.sqrt(2.0 * Fvar[..., None]) * gh_x
+    p = 0.5 * (1.0 + erf(X / np.sqrt(2.0))) * (1 - 2e-3) + 1e-3
+    logp = np.where(Y[..., None] == 1, np.log(p), np.log(1 - p))
+    return np.sum(logp * gh_w, axis=-1)
+
+
+def svgp_elbo(kern, Z, X, Y, q_mu, q_sqrt, likelihood="gaussian", lik_variance=1.0, increments=False, whiten=True,
+              num_data=None, W=None, sequences=False, jitter=JITTER):
+    """gpsig/models.py:39-73: one Kuu_Kuf_Kff call -> base_conditional -> gauss_kl -> scaled sum of var. exp. - KL."""
+    Kzz, Kzx, Kxx = Kuu_Kuf_Kff(kern, Z, X, increments=increments, jitter=jitter, full_f_cov=False, W=W,
+                                sequences=sequences)
+    fmean, fvar = base_conditional(Kzx, Kzz, Kxx, q_mu, full_cov=False, q_sqrt=np.tril(q_sqrt), white=whiten)
+    KL = gauss_kl(q_mu, np.tril(q_sqrt), None if whiten else Kzz)
+    if likelihood == "gaussian":
+        ve = gaussian_variational_expectations(fmean, fvar, Y, lik_variance)
+    else:
+        ve = bernoulli_variational_expectations(fmean, fvar, Y)
+    n = X.shape[0]
+    scale = float(num_data if num_data is not None else n) / float(n)
+    return np.sum(ve) * scale - KL, fmean, fvar
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# independent checkers (replace esig in notebooks/signature_kernel.ipynb)
+# ----------------------------------------------------------------------------------------------------------------
+def chen_signature(x, M):
+    """Truncated signature (levels 0..M, flattened) of the piecewise-linear path through x (L,d), by Chen's identity:
+    S(x) = prod_t exp(dx_t), exp(v)_m = v^{(x)m}/m!.  Same quantity as esig.tosig.stream2sig (notebook :75)."""
+    x = np.asarray(x, dtype=np.float64)
+    d = x.shape[1]
+    sig = [np.ones(())] + [np.zeros((d,) * m) for m in range(1, M + 1)]
+    for t in range(x.shape[0] - 1):
+        v = x[t + 1] - x[t]
+        e = [np.ones(())]
+        for m in range(1, M + 1):
+            e.append(np.multiply.outer(e[-1], v) / m)
+        new = []
+        for m in range(M + 1):
+            acc = np.zeros((d,) * m)
+            for a in range(m + 1):
+                acc = acc + np.multiply.outer(sig[a], e[m - a])
+            new.append(acc)
+        sig = new
+    return np.concatenate([s.reshape(-1) for s in sig])
+
+
+def rank1_tensors(Z, M):
+    """Explicit rank-1 tensors z_{m,1} (x) ... (x) z_{m,m} flattened (notebook cell 18, :180-209)."""
+    Z = np.asarray(Z, dtype=np.float64)
+    nz = Z.shape[1]
+    out = [np.ones((nz, 1))]
+    k = 0
+    for m in range(1, M + 1):
+        Zm = Z[k]
+        k += 1
+        for _ in range(1, m):
+            Zm = (Zm[..., None] * Z[k, :, None, :]).reshape(nz, -1)
+            k += 1
+        out.append(Zm)
+    return np.concatenate(out, axis=1)
+
+
+def brute_force_first_order(Delta, num_levels):
+    """K_m = sum over strictly increasing s_1<..<s_m, t_1<..<t_m of prod Delta[s_k,t_k] (tiny shapes only)."""
+    import itertools
+    L1, L2 = Delta.shape
+    K = [1.0]
+    for m in range(1, num_levels + 1):
+        tot = 0.0
+        for ss in itertools.combinations(range(L1), m):
+            for tt in itertools.combinations(range(L2), m):
+                p = 1.0
+                for a, b in zip(ss, tt):
+                    p *= Delta[a, b]
+                tot += p
+        K.append(tot)
+    return np.array(K)
