@@ -1,0 +1,82 @@
+"""
+ctypes binding of libgpsig_b200.so -- the only way the Python host reaches the device code.
+
+There is NO CPU fallback: if the library is missing it is built with nvcc (gpsig_b200/_build.py); if that fails, or a
+call is made without a CUDA device, an exception is raised.  The oracle under oracle/ is never imported from here.
+"""
+import ctypes
+import os
+
+from . import _build
+
+_c_float_p = ctypes.c_void_p  # device pointers travel as integers (torch .data_ptr())
+
+_PROTOTYPES = {
+    "gpsig_version": (ctypes.c_int, []),
+    "gpsig_error_string": (ctypes.c_char_p, [ctypes.c_int]),
+    "gpsig_last_error_detail": (ctypes.c_char_p, []),
+    "gpsig_scale_features": (ctypes.c_int, [_c_float_p, ctypes.c_long, ctypes.c_int, _c_float_p, ctypes.c_int, _c_float_p,
+                                            ctypes.c_void_p]),
+    "gpsig_gram": (ctypes.c_int, [ctypes.c_int, _c_float_p, ctypes.c_long, _c_float_p, ctypes.c_long, ctypes.c_int,
+                                  ctypes.c_void_p, _c_float_p, ctypes.c_long, ctypes.c_void_p]),
+    "gpsig_sigkern_levels": (ctypes.c_int, [_c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_long,
+                                            ctypes.c_long, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_int, _c_float_p, ctypes.c_void_p]),
+    "gpsig_seq_kern_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                         ctypes.c_size_t]),
+    "gpsig_seq_kern_levels": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, _c_float_p, ctypes.c_int, ctypes.c_int, _c_float_p,
+                                             ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, ctypes.c_long, ctypes.c_long,
+                                             ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "gpsig_mirror_upper": (ctypes.c_int, [_c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "gpsig_seq_kern_diag_levels": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, _c_float_p, ctypes.c_int, ctypes.c_int,
+                                                  ctypes.c_int, _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p,
+                                                  ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "gpsig_normalize_weight_sum": (ctypes.c_int, [_c_float_p, ctypes.c_int, ctypes.c_long, ctypes.c_long, _c_float_p, _c_float_p,
+                                                  ctypes.c_void_p, ctypes.c_float, ctypes.c_int, _c_float_p, _c_float_p,
+                                                  _c_float_p, ctypes.c_void_p]),
+    "gpsig_tensor_kern_levels": (ctypes.c_int, [_c_float_p, ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_int, _c_float_p,
+                                                ctypes.c_void_p]),
+    "gpsig_tens_vs_seq_levels": (ctypes.c_int, [_c_float_p, ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_int,
+                                                ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, ctypes.c_void_p]),
+    "gpsig_tens_seq_kern_levels": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, _c_float_p, ctypes.c_long, ctypes.c_int,
+                                                  _c_float_p, ctypes.c_long, ctypes.c_int, ctypes.c_int, _c_float_p,
+                                                  ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, ctypes.c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
+
+_lib = None
+
+
+class GPSigError(RuntimeError):
+    """A C-ABI call returned a non-zero status."""
+
+
+def library_path():
+    return _build.LIBPATH
+
+
+def load():
+    """Load (building first if needed) the shared library; raises if that is impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIBPATH
+    if not os.path.exists(path) or os.environ.get("GPSIG_B200_REBUILD"):
+        path = _build.build()
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in _PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError here = header / library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        lib = load()
+        msg = lib.gpsig_error_string(rc).decode()
+        detail = lib.gpsig_last_error_detail().decode() if rc < 0 else ""
+        raise GPSigError("%s failed: %s (%d)%s" % (what, msg, rc, (": " + detail) if detail else ""))

@@ -1,0 +1,89 @@
+// capi.cu -- C-ABI plumbing shared by every entry point: error strings, device queries, tensor-map encoding.
+#include <string.h>
+
+#include "common.cuh"
+
+namespace gpsig {
+
+static thread_local char g_detail[512] = "";
+
+void set_error_detail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_detail, sizeof(g_detail), fmt, ap);
+    va_end(ap);
+}
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_detail, sizeof(g_detail), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int num_sms() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return kNumSMsFallback;
+    if (dev != cached_dev) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = kNumSMsFallback;
+        cached = v;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_tensor_map_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                          const uint32_t* box, int swizzle128) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !sym)
+            return fail(GPSIG_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver (cudaError %d)", (int)e);
+        fn = (EncodeTiledFn)sym;
+    }
+    cuuint64_t gdims[5], gstrides[4];
+    cuuint32_t gbox[5], estr[5];
+    for (int i = 0; i < rank; ++i) { gdims[i] = dims[i]; gbox[i] = box[i]; estr[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gstrides[i] = strides_bytes[i];
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstrides, gbox, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        return fail(GPSIG_E_DRIVER,
+                    "cuTensorMapEncodeTiled failed (CUresult %d): dims=[%llu,%llu,%llu,%llu,%llu] strides=[%llu,%llu,%llu,%llu] "
+                    "box=[%u,%u,%u,%u,%u]",
+                    (int)r, (unsigned long long)gdims[0], (unsigned long long)gdims[1], (unsigned long long)gdims[2],
+                    (unsigned long long)gdims[3], (unsigned long long)gdims[4], (unsigned long long)gstrides[0],
+                    (unsigned long long)gstrides[1], (unsigned long long)gstrides[2], (unsigned long long)gstrides[3], gbox[0],
+                    gbox[1], gbox[2], gbox[3], gbox[4]);
+    }
+    return GPSIG_OK;
+}
+
+}  // namespace gpsig
+
+extern "C" int gpsig_version(void) { return GPSIG_B200_VERSION; }
+
+extern "C" const char* gpsig_error_string(int code) {
+    switch (code) {
+        case GPSIG_OK: return "ok";
+        case GPSIG_E_BADARG: return "invalid argument";
+        case GPSIG_E_UNSUPPORTED: return "unsupported configuration";
+        case GPSIG_E_WORKSPACE: return "workspace too small";
+        case GPSIG_E_ALIGN: return "alignment requirement not met";
+        case GPSIG_E_DRIVER: return "CUDA driver entry point unavailable or failed";
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "unknown error";
+}
+
+extern "C" const char* gpsig_last_error_detail(void) { return gpsig::g_detail; }

@@ -1,0 +1,492 @@
+"""
+SignatureKernel family -- same constructor kwargs (kernels.py:18-19), same 2-D (N, L*d) input convention
+(kernels.py:417-419), same public methods (K :401, Kdiag :479, K_tens :513, K_tens_vs_seq :539, K_tens_n_seq_covs :591,
+K_seq_n_seq_covs :674) and numpy-facing compute_* helpers (:141-186) as the reference.  Every method is a short
+sequence of C-ABI calls into libgpsig_b200.so; torch tensors only hold device memory.
+
+Parameters (variances, sigma, lengthscales, ...) are plain numpy values in constrained space, i.e. what the reference
+reads inside @params_as_tensors.
+"""
+import numpy as np
+import torch
+
+from . import _lib, settings
+
+_KIND = dict(linear=0, rbf=1, cosine=2, poly=3, mix=4, matern12=5, matern32=6, matern52=7)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+class SignatureKernel:
+    """Base class (kernels.py:15).  Subclasses set `_kind` and static-kernel parameters."""
+
+    _kind = None
+
+    def __init__(self, input_dim, num_features, num_levels, active_dims=None, variances=1, lengthscales=1, order=1,
+                 normalization=True, difference=True, num_lags=None, low_rank=False, num_components=50, rank_bound=None,
+                 sparsity='sqrt', name=None, device=None):
+        self.input_dim = int(input_dim)
+        self.active_dims = None if active_dims is None else np.asarray(active_dims, dtype=np.int64)
+        self.name = name
+        self.num_features = int(num_features)
+        self.num_levels = int(num_levels)
+        self.len_examples = self._validate_number_of_features(input_dim, num_features)
+        self.order = num_levels if (order <= 0 or order >= num_levels) else int(order)          # kernels.py:57
+        if self.order != 1 and low_rank:                                                         # kernels.py:59-60
+            raise NotImplementedError('Higher-order algorithms not compatible with low-rank mode (yet).')
+        self.normalization = bool(normalization)
+        self.difference = bool(difference)
+        self.variances = self._validate_signature_param("variances", variances, num_levels + 1)
+        self.sigma = 1.0
+        self.low_rank, self.num_components, self.rank_bound, self.sparsity = self._validate_low_rank_params(
+            low_rank, num_components, rank_bound, sparsity)
+        if num_lags is None:
+            self.num_lags = 0
+        else:
+            if not isinstance(num_lags, int) or num_lags < 0:                                    # kernels.py:74-75
+                raise ValueError('The variable num_lags most be a nonnegative integer or None.')
+            self.num_lags = int(num_lags)
+            if num_lags > 0:
+                self.lags = 0.1 * np.asarray(range(1, num_lags + 1), dtype=np.float64)
+                gamma = 1. / np.asarray(range(1, self.num_lags + 2), dtype=np.float64)
+                self.gamma = gamma / np.sum(gamma)
+        if lengthscales is not None:
+            self.lengthscales = self._validate_signature_param("lengthscales", lengthscales, self.num_features)
+        else:
+            self.lengthscales = None
+        self.jitter = settings.jitter
+        self.device = torch.device(device) if device is not None else None
+        self._ws = None
+
+    # ---- validators (kernels.py:94-133) ----
+    def _validate_number_of_features(self, input_dim, num_features):
+        if input_dim % num_features == 0:
+            return int(input_dim / num_features)
+        raise ValueError("The arguments num_features and input_dim are not consistent.")
+
+    def _validate_low_rank_params(self, low_rank, num_components, rank_bound, sparsity):
+        if low_rank is not None and low_rank is True:
+            if sparsity not in ['log', 'sqrt', 'lin']:
+                raise ValueError("Unknown sparsity argument %s. Possible values are 'sqrt', 'log', 'lin'" % sparsity)
+            if rank_bound is not None and rank_bound <= 0:
+                raise ValueError("The rank-bound in the low-rank algorithm must be either None or a positiv integer.")
+            if num_components is None or num_components <= 0:
+                raise ValueError("The number of components in the kernel approximation must be a positive integer.")
+            if rank_bound is None:
+                rank_bound = num_components
+        elif low_rank is not None and low_rank is not False and low_rank:
+            raise ValueError("Unknown low-rank argument: %s. It should be True of False." % low_rank)
+        else:
+            low_rank = False
+        return low_rank, num_components, rank_bound, sparsity
+
+    def _validate_signature_param(self, name, value, length):
+        value = value * np.ones(length, dtype=np.float64)
+        correct_shape = () if length == 1 else (length,)
+        if np.asarray(value).squeeze().shape != correct_shape:
+            raise ValueError("shape of parameter {} is not what is expected ({})".format(name, length))
+        return value
+
+    # ---- host helpers ----
+    def _dev(self, like=None):
+        if isinstance(like, torch.Tensor) and like.is_cuda:
+            return like.device
+        if self.device is not None:
+            return self.device
+        if not torch.cuda.is_available():
+            raise _lib.GPSigError("gpsig_b200 needs a CUDA device: there is no CPU implementation of the covariance path")
+        return torch.device("cuda", torch.cuda.current_device())
+
+    def _to_dev(self, X, like=None):
+        dev = self._dev(X if like is None else like)
+        if isinstance(X, torch.Tensor):
+            return X.to(device=dev, dtype=torch.float32)
+        return torch.as_tensor(np.ascontiguousarray(X, dtype=np.float32)).to(dev)
+
+    def _slice(self, X):
+        """gpflow Kernel._slice (kernels.py:411): pick active_dims out of the last axis."""
+        if self.active_dims is None:
+            return X
+        idx = torch.as_tensor(self.active_dims, device=X.device)
+        return X.index_select(-1, idx)
+
+    def _seqs(self, X, presliced=False):
+        X = self._to_dev(X)
+        if not presliced:
+            X = self._slice(X)
+        return X.reshape(X.shape[0], -1, self.num_features).contiguous()                        # kernels.py:417-419
+
+    def _inv_ls(self, dev):
+        if self.lengthscales is None:
+            return None
+        return torch.as_tensor((1.0 / np.asarray(self.lengthscales, dtype=np.float64)).astype(np.float32)).to(dev)
+
+    def _weights(self, dev):
+        w = float(self.sigma) * np.asarray(self.variances, dtype=np.float64)                    # kernels.py:471
+        return torch.as_tensor(w.astype(np.float32)).to(dev)
+
+    def _static_params(self):
+        return None
+
+    def _params_ptr(self):
+        p = self._static_params()
+        if p is None:
+            return None, 0
+        import ctypes
+        arr = (ctypes.c_float * len(p))(*[float(v) for v in p])
+        return arr, ctypes.cast(arr, ctypes.c_void_p).value
+
+    def _check_supported(self):
+        if self._kind is None:
+            raise NotImplementedError("use a SignatureKernel subclass (SignatureLinear, SignatureRBF, ...)")
+        if self.num_lags > 0:
+            raise NotImplementedError("lags (gpsig/lags.py) are not on the B200 path yet")
+        if self.low_rank:
+            raise NotImplementedError("low-rank mode is not on the B200 path yet")
+
+    def _workspace(self, dev, n1, L1, n2, L2, d):
+        lib = _lib.load()
+        free, _ = torch.cuda.mem_get_info(dev)
+        budget = int(min(settings.workspace_budget_bytes, max(free // 2, 64 << 20)))
+        need = lib.gpsig_seq_kern_workspace_bytes(n1, L1, n2, L2, d, budget)
+        if self._ws is None or self._ws.device != dev or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        return self._ws
+
+    # ---- device pieces (each = one C-ABI call) ----
+    def _K_seq(self, X, X2=None, row_blocks=None):
+        """kernels.py:208-237 on RAW (unscaled) sequences (N, L, d); returns level stack (M+1, N, N2).
+
+        row_blocks (symmetric only): list of (begin, end) global row ranges owned by this GPU; the result is then the
+        compact (M+1, sum of block sizes, N) stack holding only the entries j >= i of those rows (parallel.py)."""
+        lib = _lib.load()
+        dev = X.device
+        n1, L1, d = X.shape
+        n2, L2 = (n1, L1) if X2 is None else (X2.shape[0], X2.shape[1])
+        blocks = [(0, n1)] if row_blocks is None else list(row_blocks)
+        nrows = sum(e - b for b, e in blocks)
+        alloc = torch.empty if row_blocks is None else torch.zeros
+        out = alloc((self.num_levels + 1, nrows, n2), device=dev, dtype=torch.float32)
+        ws = self._workspace(dev, n1, L1, n2, L2, d)
+        inv_ls = self._inv_ls(dev)
+        keep, pptr = self._params_ptr()
+        mirror = int(X2 is None and row_blocks is None)
+        row0 = 0
+        with torch.cuda.device(dev):
+            for b, e in blocks:
+                rc = lib.gpsig_seq_kern_levels(_KIND[self._kind], pptr, X.data_ptr(), n1, L1, _ptr(X2), n2, L2, d, _ptr(inv_ls),
+                                               self.num_levels, self.order, int(self.difference), b, e, out.data_ptr(), row0,
+                                               nrows, mirror, ws.data_ptr(), ws.numel(), _stream())
+                _lib.check(rc, "gpsig_seq_kern_levels")
+                row0 += e - b
+        return out
+
+    def _K_seq_diag(self, X):
+        """kernels.py:188-205; returns (M+1, N)."""
+        lib = _lib.load()
+        dev = X.device
+        n, L, d = X.shape
+        out = torch.empty((self.num_levels + 1, n), device=dev, dtype=torch.float32)
+        ws = self._workspace(dev, min(n, 64), L, min(n, 64), L, d)
+        inv_ls = self._inv_ls(dev)
+        keep, pptr = self._params_ptr()
+        with torch.cuda.device(dev):
+            rc = lib.gpsig_seq_kern_diag_levels(_KIND[self._kind], pptr, X.data_ptr(), n, L, d, _ptr(inv_ls), self.num_levels,
+                                                self.order, int(self.difference), out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                _stream())
+        _lib.check(rc, "gpsig_seq_kern_diag_levels")
+        return out
+
+    def _finish(self, levels, diag1=None, diag2=None, symmetric=False, normalize=True, return_levels=False, diag_cols=None):
+        """kernels.py:430-433 / :455-469 / :471-476 in one launch."""
+        lib = _lib.load()
+        dev = levels.device
+        nl = levels.shape[0]
+        n1 = levels.shape[1]
+        n2 = levels.shape[2] if levels.dim() == 3 else 1
+        w = self._weights(dev)
+        lev_out = torch.empty_like(levels) if return_levels else None
+        out = None if return_levels else torch.empty(levels.shape[1:], device=dev, dtype=torch.float32)
+        sym = bool(symmetric and normalize)
+        with torch.cuda.device(dev):
+            rc = lib.gpsig_normalize_weight_sum(levels.data_ptr(), nl, n1, n2, _ptr(diag1) if normalize else 0,
+                                                _ptr(diag2) if normalize else 0, _ptr(diag_cols) if normalize else 0,
+                                                float(self.jitter), int(sym), w.data_ptr(), _ptr(lev_out), _ptr(out),
+                                                _stream())
+        _lib.check(rc, "gpsig_normalize_weight_sum")
+        return lev_out if return_levels else out
+
+    def _scale_tens(self, Z):
+        """kernels.py:366-398 (no lags): Z / lengthscales on the last axis."""
+        lib = _lib.load()
+        Z = self._to_dev(Z).contiguous()
+        inv_ls = self._inv_ls(Z.device)
+        if inv_ls is None:
+            return Z
+        out = torch.empty_like(Z)
+        d = Z.shape[-1]
+        with torch.cuda.device(Z.device):
+            rc = lib.gpsig_scale_features(Z.data_ptr(), Z.numel() // d, d, inv_ls.data_ptr(), self.num_features, out.data_ptr(),
+                                          _stream())
+        _lib.check(rc, "gpsig_scale_features")
+        return out
+
+    def _base_gram(self, A, B=None):
+        """static-kernel Gram of already-scaled points (rows, d) -> (rowsA, rowsB)  (kernels.py:225-230)."""
+        lib = _lib.load()
+        r1, d = A.shape
+        r2 = r1 if B is None else B.shape[0]
+        out = torch.empty((r1, r2), device=A.device, dtype=torch.float32)
+        keep, pptr = self._params_ptr()
+        with torch.cuda.device(A.device):
+            rc = lib.gpsig_gram(_KIND[self._kind], A.data_ptr(), r1, _ptr(B), r2, d, pptr, out.data_ptr(), r2, _stream())
+        _lib.check(rc, "gpsig_gram")
+        return out
+
+    def _K_tens(self, Zs, increments=False):
+        """kernels.py:263-283 on SCALED tensors; returns (M+1, nz, nz)."""
+        lib = _lib.load()
+        T, nz, d = Zs.shape[0], Zs.shape[1], Zs.shape[-1]
+        rows = nz * (2 if increments else 1)
+        M = torch.empty((T, rows, rows), device=Zs.device, dtype=torch.float32)
+        Zf = Zs.reshape(T, rows, d)
+        for k in range(T):
+            M[k] = self._base_gram(Zf[k])
+        out = torch.empty((self.num_levels + 1, nz, nz), device=Zs.device, dtype=torch.float32)
+        with torch.cuda.device(Zs.device):
+            rc = lib.gpsig_tensor_kern_levels(M.data_ptr(), self.num_levels, nz, nz, int(bool(increments)), out.data_ptr(),
+                                              _stream())
+        _lib.check(rc, "gpsig_tensor_kern_levels")
+        return out
+
+    def _K_tens_vs_seq(self, Z, X, increments=False):
+        """kernels.py:313-340 on RAW tensors / sequences (scaling is fused); returns (M+1, nz, n)."""
+        lib = _lib.load()
+        Z = self._to_dev(Z, like=X).contiguous()
+        nz = Z.shape[1]
+        n, L, d = X.shape
+        out = torch.empty((self.num_levels + 1, nz, n), device=X.device, dtype=torch.float32)
+        inv_ls = self._inv_ls(X.device)
+        keep, pptr = self._params_ptr()
+        with torch.cuda.device(X.device):
+            rc = lib.gpsig_tens_seq_kern_levels(_KIND[self._kind], pptr, Z.data_ptr(), nz, int(bool(increments)), X.data_ptr(),
+                                                n, L, d, _ptr(inv_ls), self.num_levels, self.order, int(self.difference),
+                                                out.data_ptr(), _stream())
+        _lib.check(rc, "gpsig_tens_seq_kern_levels")
+        return out
+
+    # ---- public API (kernels.py:400-761) ----
+    def K(self, X, X2=None, presliced=False, return_levels=False, presliced_X=False, presliced_X2=False):
+        """kernels.py:400-476."""
+        self._check_supported()
+        if presliced:
+            presliced_X = presliced_X2 = True
+        Xs = self._seqs(X, presliced_X)
+        if X2 is None:
+            lv = self._K_seq(Xs)
+            return self._finish(lv, symmetric=True, normalize=self.normalization, return_levels=return_levels)
+        X2s = self._seqs(X2, presliced_X2)
+        lv = self._K_seq(Xs, X2s)
+        d1 = d2 = None
+        if self.normalization:
+            d1, d2 = self._K_seq_diag(Xs), self._K_seq_diag(X2s)
+        return self._finish(lv, d1, d2, normalize=self.normalization, return_levels=return_levels)
+
+    def Kdiag(self, X, presliced=False, return_levels=False):
+        """kernels.py:478-510."""
+        self._check_supported()
+        n = X.shape[0]
+        if self.normalization:
+            dev = self._dev(X)
+            w = self._weights(dev)
+            if return_levels:
+                return w[:, None].expand(-1, n).contiguous()
+            return torch.full((n,), float(self.sigma * np.sum(self.variances)), device=dev, dtype=torch.float32)
+        Xs = self._seqs(X, presliced)
+        lv = self._K_seq_diag(Xs)
+        return self._finish(lv[:, :, None].contiguous(), normalize=False, return_levels=return_levels).squeeze(-1)
+
+    def K_tens(self, Z, return_levels=False, increments=False):
+        """kernels.py:512-536."""
+        self._check_supported()
+        lv = self._K_tens(self._scale_tens(Z), increments)
+        return self._finish(lv, normalize=False, return_levels=return_levels)
+
+    def K_tens_vs_seq(self, Z, X, return_levels=False, increments=False, presliced=False):
+        """kernels.py:538-588."""
+        self._check_supported()
+        Xs = self._seqs(X, presliced)
+        lv = self._K_tens_vs_seq(Z, Xs, increments)
+        d2 = self._K_seq_diag(Xs) if self.normalization else None
+        return self._finish(lv, None, d2, normalize=self.normalization, return_levels=return_levels)
+
+    def K_tens_n_seq_covs(self, Z, X, full_X_cov=False, return_levels=False, increments=False, presliced=False):
+        """kernels.py:590-671."""
+        self._check_supported()
+        Xs = self._seqs(X, presliced)
+        Kzz = self._finish(self._K_tens(self._scale_tens(Z), increments), normalize=False, return_levels=return_levels)
+        Kzx_lv = self._K_tens_vs_seq(Z, Xs, increments)
+        if full_X_cov:
+            Kxx_lv = self._K_seq(Xs)
+            dg = Kxx_lv.diagonal(dim1=1, dim2=2).contiguous() if self.normalization else None       # kernels.py:632-638
+            Kxx = self._finish(Kxx_lv, symmetric=True, normalize=self.normalization, return_levels=return_levels)
+            Kzx = self._finish(Kzx_lv, None, dg, normalize=self.normalization, return_levels=return_levels)
+        else:
+            dg = self._K_seq_diag(Xs)
+            Kzx = self._finish(Kzx_lv, None, dg, normalize=self.normalization, return_levels=return_levels)
+            if self.normalization:                                                                   # kernels.py:655-661
+                w = self._weights(Xs.device)
+                Kxx = w[:, None].expand(-1, Xs.shape[0]).contiguous()
+                if not return_levels:
+                    Kxx = torch.full((Xs.shape[0],), float(self.sigma * np.sum(self.variances)), device=Xs.device,
+                                     dtype=torch.float32)
+            else:
+                Kxx = self._finish(dg[:, :, None].contiguous(), normalize=False, return_levels=return_levels).squeeze(-1)
+        return Kzz, Kzx, Kxx
+
+    def K_seq_n_seq_covs(self, X, X2, full_X2_cov=False, return_levels=False, presliced=False, literal=False):
+        """
+        kernels.py:673-761 (InducingSequences).  X (inducing sequences) is never sliced (:679-680).  The reference
+        divides Kxx2 by sqrt(diag Kxx) twice in the normalised diagonal branch (:713 then :750);
+        literal=True reproduces that, the default divides once.  full_X2_cov with normalisation raises NameError in
+        the reference (Q2); the evident intent is implemented here.
+        """
+        self._check_supported()
+        Xa = self._to_dev(X)
+        Xa = Xa.reshape(Xa.shape[0], -1, self.num_features).contiguous()
+        Xb = self._seqs(X2, presliced)
+        Kxx_lv = self._K_seq(Xa)
+        Kxx2_lv = self._K_seq(Xa, Xb)
+        d1 = Kxx_lv.diagonal(dim1=1, dim2=2).contiguous() if self.normalization else None
+        Kxx = self._finish(Kxx_lv, symmetric=True, normalize=self.normalization, return_levels=return_levels)
+        if full_X2_cov:
+            K22_lv = self._K_seq(Xb)
+            d2 = K22_lv.diagonal(dim1=1, dim2=2).contiguous() if self.normalization else None
+            K22 = self._finish(K22_lv, symmetric=True, normalize=self.normalization, return_levels=return_levels)
+        else:
+            d2 = self._K_seq_diag(Xb)
+            if self.normalization:
+                w = self._weights(Xb.device)
+                K22 = w[:, None].expand(-1, Xb.shape[0]).contiguous()
+                if not return_levels:
+                    K22 = torch.full((Xb.shape[0],), float(self.sigma * np.sum(self.variances)), device=Xb.device,
+                                     dtype=torch.float32)
+            else:
+                K22 = self._finish(d2[:, :, None].contiguous(), normalize=False, return_levels=return_levels).squeeze(-1)
+        if self.normalization and literal and not full_X2_cov:
+            # Q4: (K / sqrt(d1 + 0)) / sqrt(d1) ... the reference's d1 here is the jittered diagonal of Kxx
+            d1sq = ((d1 + self.jitter) * (d1 + self.jitter) - self.jitter).contiguous()
+            Kxx2 = self._finish(Kxx2_lv, d1sq, d2, normalize=True, return_levels=return_levels)
+        else:
+            Kxx2 = self._finish(Kxx2_lv, d1, d2, normalize=self.normalization, return_levels=return_levels)
+        return Kxx, Kxx2, K22
+
+    # ---- numpy-facing helpers (kernels.py:141-186) ----
+    @staticmethod
+    def _np(t):
+        return t.detach().cpu().numpy()
+
+    def compute_K(self, X, Y):
+        return self._np(self.K(X, Y))
+
+    def compute_K_symm(self, X):
+        return self._np(self.K(X))
+
+    def compute_base_kern_symm(self, X):
+        """kernels.py:150-156: (N, N, L, L) static-kernel Gram of the scaled sequences."""
+        self._check_supported()
+        Xs = self._seqs(X, presliced=True)
+        n, L, d = Xs.shape
+        flat = self._scale_tens(Xs.reshape(1, n * L, d)).reshape(n * L, d)
+        M = self._base_gram(flat).reshape(n, L, n, L).permute(0, 2, 1, 3)
+        return self._np(M)
+
+    def compute_K_level_diags(self, X):
+        return self._np(self.Kdiag(X, return_levels=True))
+
+    def compute_K_levels(self, X, X2):
+        return self._np(self.K(X, X2, return_levels=True))
+
+    def compute_Kdiag(self, X):
+        return self._np(self.Kdiag(X))
+
+    def compute_K_tens(self, Z):
+        return self._np(self.K_tens(Z, return_levels=False))
+
+    def compute_K_tens_vs_seq(self, Z, X):
+        return self._np(self.K_tens_vs_seq(Z, X, return_levels=False))
+
+    def compute_K_incr_tens(self, Z):
+        return self._np(self.K_tens(Z, increments=True, return_levels=False))
+
+    def compute_K_incr_tens_vs_seq(self, Z, X):
+        return self._np(self.K_tens_vs_seq(Z, X, increments=True, return_levels=False))
+
+
+class SignatureLinear(SignatureKernel):
+    """kernels.py:786-806."""
+    _kind = "linear"
+
+
+class SignatureCosine(SignatureKernel):
+    """kernels.py:808-828."""
+    _kind = "cosine"
+
+
+class SignaturePoly(SignatureKernel):
+    """kernels.py:831-848."""
+    _kind = "poly"
+
+    def __init__(self, input_dim, num_features, num_levels, gamma=1, degree=3, **kwargs):
+        super().__init__(input_dim, num_features, num_levels, **kwargs)
+        self.gamma = float(gamma)
+        self.degree = float(degree)
+
+    def _static_params(self):
+        return [self.gamma, self.degree]
+
+
+class SignatureRBF(SignatureKernel):
+    """kernels.py:850-864."""
+    _kind = "rbf"
+
+
+SignatureGauss = SignatureRBF  # kernels.py:868
+
+
+class SignatureMix(SignatureKernel):
+    """kernels.py:870-892."""
+    _kind = "mix"
+
+    def __init__(self, input_dim, num_features, num_levels, **kwargs):
+        super().__init__(input_dim, num_features, num_levels, **kwargs)
+        self.mixing = 0.5                                                                          # kernels.py:876
+
+    def _static_params(self):
+        return [self.mixing]
+
+
+class SignatureMatern12(SignatureKernel):
+    """kernels.py:944-958."""
+    _kind = "matern12"
+
+
+class SignatureMatern32(SignatureKernel):
+    """kernels.py:964-977."""
+    _kind = "matern32"
+
+
+class SignatureMatern52(SignatureKernel):
+    """kernels.py:981-993."""
+    _kind = "matern52"
+
+
+SignatureLaplace = SignatureMatern12      # kernels.py:961
+SignatureExponential = SignatureMatern12  # kernels.py:962

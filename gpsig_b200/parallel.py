@@ -1,0 +1,125 @@
+"""
+Multi-GPU covariance: the N x N sequence-pair batch is sharded by ROW BLOCKS over ranks (one process per GPU), X is
+replicated, and the assembled covariance rows are exchanged with a single all-gather over NCCL/NVLink.
+The reference has no distributed code; this module is new.
+
+Symmetric K(X, X): a rank computes, for each row block it owns, only the tiles j >= i (C ABI: row_begin/row_end of
+gpsig_seq_kern_levels), normalises / weights / sums its rows locally (the level diagonals of ALL sequences are
+recomputed per rank -- N tiles, <1 % of the work), all-gathers the (rows, N) shards of the final matrix, and mirrors
+the lower triangle.  Row blocks are dealt in boustrophedon order (0..W-1, W-1..0, ...) so that every rank gets the same
+share of long and short rows of the triangle.  Results are bit-identical to the single-GPU symmetric path.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+def row_blocks(n, world_size, blocks_per_rank=8, multiple=8):
+    """Block boundaries [(b, e), ...] covering [0, n): about blocks_per_rank blocks per rank, sizes multiple of 8."""
+    size = -(-n // (world_size * blocks_per_rank))
+    size = max(multiple, -(-size // multiple) * multiple)
+    return [(b, min(n, b + size)) for b in range(0, n, size)]
+
+
+def owner_of_block(k, world_size):
+    """Boustrophedon dealing: block k of round r = k // W goes to rank k % W (even rounds) or W-1 - k % W (odd rounds)."""
+    r, c = divmod(k, world_size)
+    return c if r % 2 == 0 else world_size - 1 - c
+
+
+def partition(n, world_size, blocks_per_rank=8):
+    """[(rank's list of (begin, end))] for every rank."""
+    blocks = row_blocks(n, world_size, blocks_per_rank)
+    parts = [[] for _ in range(world_size)]
+    for k, be in enumerate(blocks):
+        parts[owner_of_block(k, world_size)].append(be)
+    return parts
+
+
+def rows_of(blocks):
+    if not blocks:
+        return np.zeros((0,), dtype=np.int64)
+    return np.concatenate([np.arange(b, e, dtype=np.int64) for b, e in blocks])
+
+
+def gather_rows(local_rows, n, parts, group=None):
+    """All-gather row shards (rank r holds the rows rows_of(parts[r]), shape (len, n2)) into the full (n, n2) matrix.
+
+    ONE collective: shards are padded to a common row count and exchanged with all_gather_into_tensor (NCCL); the gloo
+    backend used by the CPU tests goes through all_gather on a list."""
+    world_size = len(parts)
+    counts = [sum(e - b for b, e in p) for p in parts]
+    maxr = max(counts)
+    dev, dt, n2 = local_rows.device, local_rows.dtype, local_rows.shape[1]
+    padded = torch.zeros((maxr, n2), device=dev, dtype=dt)
+    padded[:local_rows.shape[0]] = local_rows
+    if world_size == 1:
+        gathered = padded[None]
+    elif dist.get_backend(group) == "nccl":
+        gathered = torch.empty((world_size, maxr, n2), device=dev, dtype=dt)
+        dist.all_gather_into_tensor(gathered, padded, group=group)
+    else:  # gloo (CPU tests, or two ranks sharing one GPU): stage through host memory
+        host = padded.cpu()
+        chunks = [torch.empty_like(host) for _ in range(world_size)]
+        dist.all_gather(chunks, host, group=group)
+        gathered = torch.stack(chunks).to(dev)
+    out = torch.empty((n, n2), device=dev, dtype=dt)
+    for r, p in enumerate(parts):
+        row0 = 0
+        for b, e in p:
+            out[b:e] = gathered[r, row0:row0 + (e - b)]
+            row0 += e - b
+    return out
+
+
+def sharded_K_symm(kern, X, group=None, blocks_per_rank=8, gather=True):
+    """K(X, X) (kernels.py:400-476, X2 is None) with the pair batch sharded over the process group.
+
+    Returns the full (N, N) matrix on every rank; gather=False returns (local rows (len, N) with only j >= i valid,
+    row indices) without communicating."""
+    kern._check_supported()
+    ws = dist.get_world_size(group) if dist.is_initialized() else 1
+    rk = dist.get_rank(group) if dist.is_initialized() else 0
+    Xs = kern._seqs(X)
+    n = Xs.shape[0]
+    parts = partition(n, ws, blocks_per_rank)
+    mine = parts[rk]
+    rows = rows_of(mine)
+    dev = Xs.device
+    if len(rows):
+        lv = kern._K_seq(Xs, row_blocks=mine)                                   # (M+1, len(rows), N), j >= i only
+        if kern.normalization:
+            dg = kern._K_seq_diag(Xs)                                           # (M+1, N)
+            ridx = torch.as_tensor(rows, device=dev)
+            d1 = dg.index_select(1, ridx).contiguous()
+            cols = ridx.to(torch.int32).contiguous()
+            local = kern._finish(lv, d1, dg, normalize=True, diag_cols=cols)
+        else:
+            local = kern._finish(lv, normalize=False)
+    else:
+        local = torch.zeros((0, n), device=dev, dtype=torch.float32)
+    if not gather:
+        return local, rows
+    K = gather_rows(local, n, parts, group)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        rc = lib.gpsig_mirror_upper(K.data_ptr(), 1, n, torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "gpsig_mirror_upper")
+    return K
+
+
+def sharded_K(kern, X, X2=None, group=None, blocks_per_rank=8):
+    """K(X, X2): symmetric case -> sharded_K_symm; rectangular case shards the rows of X (contiguous blocks dealt the same
+    way, no triangle to balance) and all-gathers."""
+    if X2 is None:
+        return sharded_K_symm(kern, X, group, blocks_per_rank)
+    ws = dist.get_world_size(group) if dist.is_initialized() else 1
+    rk = dist.get_rank(group) if dist.is_initialized() else 0
+    n = X.shape[0]
+    parts = partition(n, ws, blocks_per_rank)
+    rows = rows_of(parts[rk])
+    Xr = X[torch.as_tensor(rows, device=X.device)] if isinstance(X, torch.Tensor) else X[rows]
+    local = kern.K(Xr, X2) if len(rows) else torch.zeros((0, X2.shape[0]), device=kern._dev(), dtype=torch.float32)
+    return gather_rows(local, n, parts, group)

@@ -1,0 +1,128 @@
+"""
+GPU parity at sizes past the golden fixtures: BASELINE.json's configs at reduced N against the oracle, the headline
+tile shape (L=128, d=8, M=5), chunked workspaces, and size-independent properties at full N.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gpsig_oracle as O
+from util import assert_close, assert_levels_close, random_walks
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(kind, L, d, M, **kw):
+    from gpsig_b200 import kernels
+    cls = dict(linear=kernels.SignatureLinear, rbf=kernels.SignatureRBF)[kind]
+    k = cls(L * d, d, M, **kw)
+    ko = O.SignatureKernelOracle(kind, L * d, d, M, **kw)
+    return k, ko
+
+
+def test_config1_rbf_n32_l20_d3_m3():
+    """BASELINE.json configs[0]: SignatureRBF K(X,X) N=32 L=20 d=3 M=3."""
+    X = random_walks(32, 20, 3, 0).reshape(32, -1)
+    ls = np.array([0.9, 1.1, 1.4])
+    for norm in (True, False):
+        k, ko = _pair("rbf", 20, 3, 3, lengthscales=ls, normalization=norm)
+        assert_close(k.compute_K_symm(X), ko.K(X), msg="cfg1 norm=%s" % norm)
+        assert_levels_close(k.compute_K_levels(X, X[:7]), ko.K(X, X[:7], return_levels=True), msg="cfg1 rect")
+    k, ko = _pair("linear", 20, 3, 3, order=3, normalization=False, lengthscales=None)
+    assert_close(k.compute_K_symm(X), ko.K(X), msg="cfg1 order=M")
+
+
+@pytest.mark.parametrize("kind", ["linear", "rbf"])
+def test_config2_shape_subsampled(kind):
+    """configs[1] tile shape (L=64, d=6, M=4) on 96 sequences (the oracle needs N^2 L^2 doubles)."""
+    X = random_walks(96, 64, 6, 1).reshape(96, -1)
+    k, ko = _pair(kind, 64, 6, 4)
+    assert_close(k.compute_K_symm(X), ko.K(X, row_block=16), msg="cfg2")
+
+
+@pytest.mark.parametrize("kind", ["linear", "rbf"])
+def test_headline_tile_shape_subsampled(kind):
+    """configs[3] tile shape (L=128, d=8, M=5) on 48 sequences, symmetric and rectangular, levels and sum."""
+    X = random_walks(48, 128, 8, 2).reshape(48, -1)
+    Y = random_walks(21, 128, 8, 3).reshape(21, -1)
+    ls = np.sqrt(8.0) * np.ones(8) if kind == "rbf" else np.ones(8)
+    k, ko = _pair(kind, 128, 8, 5, lengthscales=ls)
+    assert_levels_close(k.K(X, return_levels=True).cpu().numpy(), ko.K(X, return_levels=True, row_block=8), msg="symm")
+    assert_close(k.compute_K(X, Y), ko.K(X, Y, row_block=8), msg="rect")
+    k2, ko2 = _pair(kind, 128, 8, 5, lengthscales=ls, normalization=False)
+    assert_levels_close(k2.K(X, return_levels=True).cpu().numpy(), ko2.K(X, return_levels=True, row_block=8), msg="raw")
+
+
+def test_chunked_workspace_gives_identical_result():
+    """A tiny workspace budget forces many row-block chunks; the result must not change by a single bit."""
+    from gpsig_b200 import settings
+    X = random_walks(70, 64, 4, 4).reshape(70, -1)
+    k, _ = _pair("rbf", 64, 4, 4)
+    ref = k.K(X).clone()
+    old = settings.workspace_budget_bytes
+    try:
+        settings.workspace_budget_bytes = 3 << 20
+        k._ws = None
+        got = k.K(X)
+        got_rect = k.K(X, X[:33])
+    finally:
+        settings.workspace_budget_bytes = old
+        k._ws = None
+    assert torch.equal(ref, got)
+    assert_close(got_rect.cpu().numpy(), ref[:, :33].cpu().numpy(), tol=1e-5)
+
+
+def test_kuf_shape_subsampled_vs_oracle():
+    """configs[2] shape (L=128, d=8, M=5) with 32 inducing tensors and 64 sequences, increments on and off."""
+    rng = np.random.default_rng(5)
+    X = random_walks(64, 128, 8, 5).reshape(64, -1)
+    T = 15
+    for inc in (False, True):
+        Z = 0.5 * rng.standard_normal((T, 32, 2, 8) if inc else (T, 32, 8))
+        for kind in ("linear", "rbf"):
+            k, ko = _pair(kind, 128, 8, 5, lengthscales=2.0 * np.ones(8))
+            got = k.K_tens_vs_seq(Z, X, increments=inc, return_levels=True).cpu().numpy()
+            assert_levels_close(got, ko.K_tens_vs_seq(Z, X, increments=inc, return_levels=True), msg="Kuf %s" % kind)
+            Kzz, Kzx, Kxx = k.K_tens_n_seq_covs(Z, X, increments=inc)
+            rzz, rzx, rxx = ko.K_tens_n_seq_covs(Z, X, increments=inc)
+            assert_close(Kzz.cpu().numpy(), rzz, msg="Kzz")
+            assert_close(Kzx.cpu().numpy(), rzx, msg="Kzx")
+            assert_close(Kxx.cpu().numpy(), rxx, msg="Kxx")
+
+
+def test_full_size_properties_n1024():
+    """configs[1] at full size (N=1024, L=64, d=6, M=4): symmetry, unit diagonal, positive semi-definiteness (via
+    Cholesky of K + 1e-4 I), and a 32x32 corner against the oracle."""
+    X = random_walks(1024, 64, 6, 6).reshape(1024, -1)
+    k, ko = _pair("linear", 64, 6, 4)
+    K = k.K(X)
+    assert torch.equal(K, K.T)
+    assert torch.allclose(torch.diagonal(K), torch.full((1024,), 5.0, device=K.device), atol=1e-4)
+    torch.linalg.cholesky(K.double() + 1e-4 * torch.eye(1024, device=K.device, dtype=torch.float64))
+    assert_close(K[:32, :32].cpu().numpy(), ko.K(X[:32]), msg="corner")
+    # rectangular call on the same data agrees with the symmetric one off the diagonal
+    Kr = k.K(X[:64], X[64:256])
+    assert_close(Kr.cpu().numpy(), K[:64, 64:256].cpu().numpy(), tol=1e-5)
+
+
+def test_svgp_elbo_vs_oracle():
+    """gpsig/models.py:39-73 consumer: ELBO and predictive moments on a small problem (fp32 device vs fp64 oracle)."""
+    from gpsig_b200 import kernels, inducing_variables as iv, models
+    rng = np.random.default_rng(7)
+    n, L, d, M, nz = 60, 32, 3, 3, 10
+    X = random_walks(n, L, d, 7).reshape(n, -1)
+    Y = (rng.standard_normal((n, 1)) > 0).astype(np.float64)
+    Z = 0.4 * rng.standard_normal((6, nz, 2, d))
+    q_mu = 0.3 * rng.standard_normal((nz, 1))
+    q_sqrt = np.tril(0.2 * rng.standard_normal((1, nz, nz))) + np.eye(nz)[None]
+    k = kernels.SignatureRBF(L * d, d, M, lengthscales=1.5)
+    ko = O.SignatureKernelOracle("rbf", L * d, d, M, lengthscales=1.5)
+    feat = iv.InducingTensors(Z, M, increments=True)
+    for lik, name in ((models.Gaussian(0.5), "gaussian"), (models.Bernoulli(), "bernoulli")):
+        m = models.SVGP(X, Y, k, lik, feat, num_latent=1, q_mu=q_mu, q_sqrt=q_sqrt)
+        elbo = m.compute_log_likelihood()
+        ref, fm, fv = O.svgp_elbo(ko, Z, X, Y, q_mu, q_sqrt, likelihood=name, lik_variance=0.5, increments=True)
+        assert abs(elbo - ref) / abs(ref) < 2e-4, (elbo, ref)
+        mu, var = m.predict_f(X)
+        assert_close(mu.cpu().numpy(), fm, tol=2e-4, msg="fmean")
+        assert_close(var.cpu().numpy(), fv, tol=2e-4, msg="fvar")

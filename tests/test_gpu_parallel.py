@@ -1,0 +1,69 @@
+"""GPU: the row-sharded multi-GPU path.  World size 1 in-process, and world size 2 as two processes (NCCL when two
+devices are visible, otherwise both ranks share cuda:0 and exchange through gloo) -- the sharded result must be
+bit-identical to the single-GPU symmetric result."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from util import random_walks
+
+pytestmark = pytest.mark.gpu
+
+
+def _kernel():
+    from gpsig_b200 import kernels
+    return kernels.SignatureRBF(64 * 4, 4, 4, lengthscales=1.3)
+
+
+def test_sharded_world_size_1_matches_single():
+    from gpsig_b200 import parallel
+    X = random_walks(150, 64, 4, 11).reshape(150, -1)
+    k = _kernel()
+    assert torch.equal(parallel.sharded_K_symm(k, X), k.K(X))
+    k.normalization = False
+    assert torch.equal(parallel.sharded_K_symm(k, X), k.K(X))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, ws, port, q):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    ndev = torch.cuda.device_count()
+    backend = "nccl" if ndev >= ws else "gloo"
+    torch.cuda.set_device(rank % ndev)
+    dist.init_process_group(backend, rank=rank, world_size=ws)
+    from gpsig_b200 import parallel
+    X = random_walks(150, 64, 4, 11).reshape(150, -1)
+    k = _kernel()
+    K = parallel.sharded_K_symm(k, X)
+    ref = k.K(X)
+    q.put((rank, bool(torch.equal(K, ref)), backend))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_world_size_2_matches_single():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=120)
+    assert sorted(r[:2] for r in res) == [(0, True), (1, True)], res

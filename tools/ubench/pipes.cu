@@ -52,6 +52,41 @@ __global__ void __launch_bounds__(256) k(float* out, long long* cyc, float seed)
         } else if (MODE == 7) {  // FMUL
 #pragma unroll
             for (int i = 0; i < 16; ++i) a[i] = a[i] * b;
+        } else if (MODE == 9) {  // FADD2 packed: 8 packed ops = 16 adds
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+                unsigned long long A, B;
+                asm volatile("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a[i]), "f"(a[i + 1]));
+                asm volatile("mov.b64 %0, {%1, %2};" : "=l"(B) : "f"(b), "f"(c));
+                asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(A) : "l"(A), "l"(B));
+                asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(a[i]), "=f"(a[i + 1]) : "l"(A));
+            }
+        } else if (MODE == 10) {  // dependent-chain mix like the recursion: per j: t=A+O (FADD2), A+=p (FADD2), p=fma(d,t,p) (FFMA2)
+            unsigned long long P, O, D;
+            asm volatile("mov.b64 %0, {%1, %2};" : "=l"(P) : "f"(b), "f"(c));
+            asm volatile("mov.b64 %0, {%1, %2};" : "=l"(O) : "f"(c), "f"(b));
+            asm volatile("mov.b64 %0, {%1, %2};" : "=l"(D) : "f"(b), "f"(b));
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+                unsigned long long A, T;
+                asm volatile("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a[i]), "f"(a[i + 1]));
+                asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(T) : "l"(A), "l"(O));
+                asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(A) : "l"(A), "l"(P));
+                asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(P) : "l"(D), "l"(T), "l"(P));
+                asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(a[i]), "=f"(a[i + 1]) : "l"(A));
+            }
+            float p0, p1;
+            asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(p0), "=f"(p1) : "l"(P));
+            b = p0 * 1e-30f + 1.0001f; c = p1 * 1e-30f + 0.5f;
+        } else if (MODE == 11) {  // same chain, scalar: 16 x (FADD, FADD, FFMA)
+            float p = b, o = c;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                float t = a[i] + o;
+                a[i] += p;
+                p = fmaf(b, t, p);
+            }
+            c = p * 1e-30f + 0.5f;
         } else if (MODE == 8) {  // FSEL-like select
 #pragma unroll
             for (int i = 0; i < 16; ++i) a[i] = (it & (1 << (i & 7))) ? a[i] : c;
@@ -96,6 +131,9 @@ int main() {
         run<4>("LDS.128 (+4 FADD each)", 4, w);
         run<5>("mix 12 FFMA + 4 SHFL", 16, w);
         run<8>("FSEL", 16, w);
+        run<9>("FADD2 (8 packed = 16 add)", 8, w);
+        run<10>("chain packed 24 ops(48 flop-lanes)", 24, w);
+        run<11>("chain scalar 48 ops", 48, w);
     }
     return 0;
 }
