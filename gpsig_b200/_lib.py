@@ -15,6 +15,11 @@ _PROTOTYPES = {
     "gpsig_version": (ctypes.c_int, []),
     "gpsig_error_string": (ctypes.c_char_p, [ctypes.c_int]),
     "gpsig_last_error_detail": (ctypes.c_char_p, []),
+    "gpsig_launch_count": (ctypes.c_longlong, []),
+    "gpsig_profile_enable": (ctypes.c_int, [ctypes.c_int]),
+    "gpsig_profile_reset": (ctypes.c_int, []),
+    "gpsig_profile_read": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong),
+                                          ctypes.POINTER(ctypes.c_double)]),
     "gpsig_scale_features": (ctypes.c_int, [_c_float_p, ctypes.c_long, ctypes.c_int, _c_float_p, ctypes.c_int, _c_float_p,
                                             ctypes.c_void_p]),
     "gpsig_gram": (ctypes.c_int, [ctypes.c_int, _c_float_p, ctypes.c_long, _c_float_p, ctypes.c_long, ctypes.c_int,

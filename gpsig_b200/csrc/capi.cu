@@ -1,6 +1,10 @@
 // capi.cu -- C-ABI plumbing shared by every entry point: error strings, device queries, tensor-map encoding.
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 namespace gpsig {
@@ -20,6 +24,30 @@ int fail(int code, const char* fmt, ...) {
     vsnprintf(g_detail, sizeof(g_detail), fmt, ap);
     va_end(ap);
     return code;
+}
+
+// ---- launch counter and per-class event timing --------------------------------------------------------------------
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+struct ProfRec { int cls; double units; cudaEvent_t e0, e1; };
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec*> g_prof_recs;
+
+ProfScope::ProfScope(int cls_, cudaStream_t st_, double units) : cls(cls_), st(st_), rec(nullptr) {
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    ProfRec* r = new ProfRec{cls_, units, nullptr, nullptr};
+    if (cudaEventCreate(&r->e0) != cudaSuccess || cudaEventCreate(&r->e1) != cudaSuccess) { delete r; return; }
+    cudaEventRecord(r->e0, st);
+    rec = r;
+}
+ProfScope::~ProfScope() {
+    if (!rec) return;
+    ProfRec* r = (ProfRec*)rec;
+    cudaEventRecord(r->e1, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_recs.push_back(r);
 }
 
 int num_sms() {
@@ -70,6 +98,45 @@ int encode_tensor_map_f32(CUtensorMap* out, const void* base, int rank, const ui
 }
 
 }  // namespace gpsig
+
+extern "C" long long gpsig_launch_count(void) { return gpsig::g_launches.load(); }
+
+extern "C" int gpsig_profile_enable(int on) {
+    gpsig::g_prof_on.store(on ? 1 : 0);
+    return GPSIG_OK;
+}
+
+extern "C" int gpsig_profile_reset(void) {
+    std::lock_guard<std::mutex> lk(gpsig::g_prof_mu);
+    for (gpsig::ProfRec* r : gpsig::g_prof_recs) {
+        cudaEventSynchronize(r->e1);
+        cudaEventDestroy(r->e0);
+        cudaEventDestroy(r->e1);
+        delete r;
+    }
+    gpsig::g_prof_recs.clear();
+    return GPSIG_OK;
+}
+
+extern "C" int gpsig_profile_read(int cls, double* total_ms, long long* launches, double* units) {
+    if (cls < 0 || cls >= GPSIG_PROF_NUM_CLASSES) return gpsig::fail(GPSIG_E_BADARG, "profile_read: unknown class %d", cls);
+    double ms = 0.0, un = 0.0;
+    long long n = 0;
+    std::lock_guard<std::mutex> lk(gpsig::g_prof_mu);
+    for (gpsig::ProfRec* r : gpsig::g_prof_recs) {
+        if (r->cls != cls) continue;
+        cudaError_t e = cudaEventSynchronize(r->e1);
+        if (e != cudaSuccess) return (int)e;
+        float t = 0.f;
+        e = cudaEventElapsedTime(&t, r->e0, r->e1);
+        if (e != cudaSuccess) return (int)e;
+        ms += t; un += r->units; ++n;
+    }
+    if (total_ms) *total_ms = ms;
+    if (launches) *launches = n;
+    if (units) *units = un;
+    return GPSIG_OK;
+}
 
 extern "C" int gpsig_version(void) { return GPSIG_B200_VERSION; }
 

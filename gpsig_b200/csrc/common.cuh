@@ -16,10 +16,24 @@ constexpr int kNumSMsFallback = 148;
 void set_error_detail(const char* fmt, ...);
 int fail(int code, const char* fmt, ...);
 int num_sms();
+void count_launch();  // every kernel launch of the library passes through check_launch(): gpsig_launch_count()
 inline int check_launch() {
+    count_launch();
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? GPSIG_OK : (int)e;
 }
+
+// ---- measurement hooks (gpsig_profile_*): CUDA events around one kernel launch on its own stream ------------------
+// Inactive (two predictable branches) unless gpsig_profile_enable(1) was called.  `units` is the number of work units
+// the launch processes (sequence pairs for the recursion / producer) so that bench.py can turn the measured
+// durations into algorithmic bytes per second.
+struct ProfScope {
+    int cls;
+    cudaStream_t st;
+    void* rec;
+    ProfScope(int cls, cudaStream_t st, double units);
+    ~ProfScope();
+};
 
 // ---- device-side PTX helpers ---------------------------------------------------------------------------------------
 #if defined(__CUDACC__)

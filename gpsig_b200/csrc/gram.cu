@@ -194,6 +194,7 @@ static int launch_producer_kind(const ProdParams& p, int DP, bool diff2d, cudaSt
 // kind LINEAR with difference: the caller passes time INCREMENTS as A/B and diff2d = false (Delta = <dx_s, dy_t>,
 // kernels.py:226 + signature_algs.py:26 by bilinearity); every other kind passes scaled points and diff2d = difference.
 int launch_delta_producer(int kind, const ProdParams& p, int DP, bool diff2d, cudaStream_t st) {
+    ProfScope prof(GPSIG_PROF_PRODUCER, st, p.diag ? (double)p.nj : (double)p.ni * p.nj);
     switch (kind) {
         case GPSIG_KERN_LINEAR: return launch_producer_kind<GPSIG_KERN_LINEAR>(p, DP, diff2d, st);
         case GPSIG_KERN_RBF: return launch_producer_kind<GPSIG_KERN_RBF>(p, DP, diff2d, st);
@@ -211,6 +212,7 @@ int launch_prep_points(const float* X, long long n, int L, int d, const float* i
                        float* norms, cudaStream_t st) {
     const long long total = n * (long long)(increments ? L - 1 : L);
     if (total <= 0) return GPSIG_OK;
+    ProfScope prof(GPSIG_PROF_PREP, st, (double)n);
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)num_sms() * 16;
     prep_points_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(X, n, L, d, inv_ls, increments, DP, out, norms);

@@ -196,6 +196,7 @@ extern "C" int gpsig_seq_kern_levels(int kind, const float* params, const float*
         i0 += (int)ib;
     }
     if (mirror && n1 > 1) {
+        ProfScope prof(GPSIG_PROF_EPILOGUE, st, (double)per_level * nl);
         mirror_upper_kernel<<<grid_for(per_level * nl, 256), 256, 0, st>>>(out_levels, n1, nl);
         rc = check_launch();
     }
@@ -279,6 +280,7 @@ extern "C" int gpsig_sigkern_levels(const float* M, int n1, int L1, int n2, int 
 
 extern "C" int gpsig_mirror_upper(float* levels, int nl, int n, void* stream) {
     if (!levels || nl < 1 || n < 1) return fail(GPSIG_E_BADARG, "mirror_upper: bad arguments");
+    ProfScope prof(GPSIG_PROF_EPILOGUE, (cudaStream_t)stream, (double)n * n * nl);
     mirror_upper_kernel<<<grid_for((long long)n * n * nl, 256), 256, 0, (cudaStream_t)stream>>>(levels, n, nl);
     return check_launch();
 }
@@ -291,6 +293,7 @@ extern "C" int gpsig_normalize_weight_sum(const float* levels, int nl, long n1, 
     if (symmetric && n1 != n2) return fail(GPSIG_E_BADARG, "symmetric normalisation needs a square matrix");
     if (symmetric && levels_out == levels)
         return fail(GPSIG_E_BADARG, "symmetric normalisation reads the diagonal: levels_out must not alias levels");
+    ProfScope prof(GPSIG_PROF_EPILOGUE, (cudaStream_t)stream, (double)n1 * n2);
     normalize_weight_sum_kernel<<<grid_for((long long)n1 * n2, 256), 256, 0, (cudaStream_t)stream>>>(
         levels, nl, n1, n2, diag1, diag2, diag_cols, jitter, symmetric, weights, levels_out, out_sum);
     return check_launch();

@@ -529,6 +529,7 @@ int launch_sigkern_fo(const float* M, int n1, int Lrows, int n2, int ncols, int 
         long long want = (p.nitems + nwarps - 1) / nwarps;
         int grid = (int)(want < num_sms() ? want : num_sms());
         if (grid < 1) grid = 1;
+        ProfScope prof(GPSIG_PROF_RECURSION, st, (double)p.nitems * p.G);
         return difference ? launch_tma_lev<true>(nlev, tmap, p, nwarps, smem, grid, st)
                           : launch_tma_lev<false>(nlev, tmap, p, nwarps, smem, grid, st);
     }
@@ -553,6 +554,7 @@ int launch_sigkern_fo(const float* M, int n1, int Lrows, int n2, int ncols, int 
     long long npairs = (long long)n1 * n2;
     long long blocks = (npairs + nwarps - 1) / nwarps;
     int grid = (int)(blocks < (long long)num_sms() * 8 ? blocks : (long long)num_sms() * 8);
+    ProfScope prof(GPSIG_PROF_RECURSION_OTHER, st, (double)npairs);
     sigkern_fo_generic_kernel<<<grid, nwarps * 32, smem, st>>>(g);
     return check_launch();
 }
@@ -579,6 +581,7 @@ int launch_sigkern_ho(const float* M, int n1, int Lrows, int n2, int ncols, long
     const long long npairs = (long long)n1 * n2;
     long long blocks = (npairs + ppb - 1) / ppb;
     const long long cap = (long long)num_sms() * 8;
+    ProfScope prof(GPSIG_PROF_RECURSION_OTHER, st, (double)npairs);
     sigkern_ho_serial_kernel<<<(int)(blocks < cap ? blocks : cap), ppb, smem, st>>>(h);
     return check_launch();
 }

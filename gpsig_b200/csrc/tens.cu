@@ -199,6 +199,7 @@ static int launch_tsf(const TsfParams& p, cudaStream_t st) {
     const int T = p.nlev * (p.nlev + 1) / 2, ninc = p.increments ? 2 : 1;
     const size_t smem = (size_t)T * ninc * (p.DP + 1) * sizeof(float);
     dim3 grid((unsigned)((p.n + 127) / 128), (unsigned)p.nz);
+    ProfScope prof(GPSIG_PROF_TENS, st, (double)p.nz * p.n);
     auto k = tens_seq_fused_kernel<KIND>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<grid, 128, smem, st>>>(p);
@@ -231,6 +232,7 @@ extern "C" int gpsig_tens_vs_seq_levels(const float* M, int num_levels, long nz,
     const long long per = (long long)nz * n;
     long long blocks = (per + 127) / 128;
     const long long cap = (long long)num_sms() * 16;
+    ProfScope prof(GPSIG_PROF_TENS, (cudaStream_t)stream, (double)per);
     tens_vs_seq_kernel<<<(int)(blocks < cap ? blocks : cap), 128, 0, (cudaStream_t)stream>>>(p);
     return check_launch();
 }

@@ -204,14 +204,15 @@ class SignatureKernel:
         _lib.check(rc, "gpsig_seq_kern_diag_levels")
         return out
 
-    def _finish(self, levels, diag1=None, diag2=None, symmetric=False, normalize=True, return_levels=False, diag_cols=None):
+    def _finish(self, levels, diag1=None, diag2=None, symmetric=False, normalize=True, return_levels=False, diag_cols=None,
+                unit_weights=False):
         """kernels.py:430-433 / :455-469 / :471-476 in one launch."""
         lib = _lib.load()
         dev = levels.device
         nl = levels.shape[0]
         n1 = levels.shape[1]
         n2 = levels.shape[2] if levels.dim() == 3 else 1
-        w = self._weights(dev)
+        w = torch.ones(nl, device=dev, dtype=torch.float32) if unit_weights else self._weights(dev)
         lev_out = torch.empty_like(levels) if return_levels else None
         out = None if return_levels else torch.empty(levels.shape[1:], device=dev, dtype=torch.float32)
         sym = bool(symmetric and normalize)
@@ -381,9 +382,9 @@ class SignatureKernel:
             else:
                 K22 = self._finish(d2[:, :, None].contiguous(), normalize=False, return_levels=return_levels).squeeze(-1)
         if self.normalization and literal and not full_X2_cov:
-            # Q4: (K / sqrt(d1 + 0)) / sqrt(d1) ... the reference's d1 here is the jittered diagonal of Kxx
-            d1sq = ((d1 + self.jitter) * (d1 + self.jitter) - self.jitter).contiguous()
-            Kxx2 = self._finish(Kxx2_lv, d1sq, d2, normalize=True, return_levels=return_levels)
+            # Q4: Kxx2 is divided by sqrt(diag Kxx + jitter) at :713 and again at :750 -- two normalisation launches
+            once = self._finish(Kxx2_lv, d1, None, normalize=True, return_levels=True, unit_weights=True)
+            Kxx2 = self._finish(once, d1, d2, normalize=True, return_levels=return_levels)
         else:
             Kxx2 = self._finish(Kxx2_lv, d1, d2, normalize=self.normalization, return_levels=return_levels)
         return Kxx, Kxx2, K22

@@ -51,6 +51,28 @@ const char* gpsig_error_string(int code);
 const char* gpsig_last_error_detail(void);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Measurement hooks (no reference counterpart: the reference has no profiling subsystem).
+ *   gpsig_launch_count(): number of kernels this library has launched since it was loaded (monotone, all threads).
+ *   gpsig_profile_enable(1): from now on every launch of the classes below is bracketed by two CUDA events on the
+ *     stream it is launched on; gpsig_profile_read() synchronises those events and returns, for one class, the summed
+ *     device time, the number of launches and the work units they processed (sequence pairs / (z, n) pairs);
+ *     gpsig_profile_reset() drops the records.  Disabled by default (zero overhead beyond one relaxed load).
+ * ------------------------------------------------------------------------------------------------------------- */
+enum {
+    GPSIG_PROF_PREP = 0,       /* scaling / time increments / norms of the points */
+    GPSIG_PROF_PRODUCER = 1,   /* increment-Gram chunk producer (a3 + signature_algs.py:26) */
+    GPSIG_PROF_RECURSION = 2,  /* TMA-staged first-order recursion (a4) -- the dominant kernel */
+    GPSIG_PROF_RECURSION_OTHER = 3, /* generic first-order and higher-order recursions (a4 fallback, a5) */
+    GPSIG_PROF_EPILOGUE = 4,   /* normalise / weight / sum, mirror (a7) */
+    GPSIG_PROF_TENS = 5,       /* inducing-tensor kernels (a9-a11) */
+    GPSIG_PROF_NUM_CLASSES = 6
+};
+long long gpsig_launch_count(void);
+int gpsig_profile_enable(int on);
+int gpsig_profile_reset(void);
+int gpsig_profile_read(int cls, double* total_ms, long long* launches, double* units);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * a2  kernels.py:342-364 (_apply_scaling_and_lags_to_sequences, no-lags branch) and :366-398 (tensors):
  *     out[r, c] = X[r, c] * inv_lengthscales[c % num_features]        (inv_lengthscales may be NULL = copy)
  * ------------------------------------------------------------------------------------------------------------- */
