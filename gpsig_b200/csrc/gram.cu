@@ -103,7 +103,17 @@ __global__ void __launch_bounds__(256) delta_producer_kernel(const ProdParams p)
         if (!p.diag && p.upper_only && group_last_j < i) continue;
         float* orow = p.diag ? p.out + (long long)jl * p.P + t0
                              : p.out + (((long long)ii * p.out_rows) * p.nj + jl) * p.P + t0;
-        const long long row_stride = (long long)p.nj * p.P;
+        long long row_stride = (long long)p.nj * p.P;
+        if (p.stream) {  // consumer-ready layout: stream u % NW, position u / NW, skewed row s + strip, swizzled chunk
+            const int jgl = jl / p.G, q = jl - jgl * p.G;
+            const long long u = p.diag ? (long long)jgl
+                                       : items_before(ii, p.njg, p.G, p.upper_only, p.i0, p.j0) + jgl -
+                                             first_group(ii, p.G, p.upper_only, p.i0, p.j0);
+            const long long w = u % p.NW, n = u / p.NW;
+            const uint32_t sw = swizzle_in_row((uint32_t)(q * p.P + t0) * 4u);
+            orow = p.out + (w * p.SR + n * p.out_rows + (t0 >> 4)) * kSkewRowFloats + (sw >> 2);
+            row_stride = kSkewRowFloats;
+        }
         float fprev[NPT];
 #pragma unroll
         for (int u = 0; u < NPT; ++u) fprev[u] = 0.f;

@@ -8,6 +8,47 @@ struct KernParams {
     float a, b;  // poly: gamma, degree; mix: mixing
 };
 
+// ---- work-item enumeration shared by the chunk producer and the recursion kernels ---------------------------------
+// An item is a group of G neighbouring pairs (i, jg*G .. jg*G+G-1).  Items are numbered row by row.
+// sum_{x < i} floor(x / G)
+__host__ __device__ inline long long tri_floor(long long i, int G) {
+    long long b = i / G, r = i % G;
+    return (long long)G * b * (b - 1) / 2 + r * b;
+}
+// number of items in local rows < il.  With upper_only, local row il keeps the groups whose GLOBAL group index is
+// >= floor((i_off + il) / G); the chunk starts at global group j_off / G.
+__host__ __device__ inline long long items_before(int il, int njg, int G, int upper_only, int i_off, int j_off) {
+    if (!upper_only) return (long long)il * njg;
+    long long skipped = tri_floor((long long)i_off + il, G) - tri_floor(i_off, G) - (long long)il * (j_off / G);
+    return (long long)il * njg - skipped;
+}
+
+// the chunk's local group index of the first group row il keeps
+__host__ __device__ inline int first_group(int il, int G, int upper_only, int i_off, int j_off) {
+    return upper_only ? (i_off + il) / G - j_off / G : 0;
+}
+
+// ---- consumer-ready stream layout of the increment-Gram chunk (written by gram.cu, read by sigstream.cu) -----------
+// Item u belongs to stream u % NW (one stream per consumer warp of the recursion launch) at position u / NW.  A stream
+// is a sequence of 2 KB "skewed rows": skewed row n*rows + s + l holds, for each of the G pairs of item n, the 16-column
+// strip l of increment row s -- so at step T every lane of the consumer warp reads the SAME skewed row T, and rows are
+// contiguous in memory (large 1-D bulk copies).  Inside a skewed row the 16-byte chunks are XOR-swizzled over 128-byte
+// lines exactly like CU_TENSOR_MAP_SWIZZLE_128B, which makes the strip-wise LDS.128 reads bank-conflict free.
+constexpr int kSkewRowFloats = 512;  // 2048 bytes
+struct StreamGeom {
+    int NW;         // streams (consumer warps in the grid)
+    long long SR;   // skewed rows per stream (pitch)
+    int R;          // skewed rows per bulk copy / smem stage
+    int S;          // stages per consumer ring
+    int ncw;        // consumer warps per CTA
+    int grid;
+};
+StreamGeom stream_geometry(long long nitems, int rows, int LP);
+inline size_t stream_bytes(const StreamGeom& g) { return (size_t)g.NW * (size_t)g.SR * 2048; }
+__host__ __device__ inline uint32_t swizzle_in_row(uint32_t byte_in_row) {
+    return ((byte_in_row >> 7) << 7) | ((((byte_in_row >> 4) & 7u) ^ ((byte_in_row >> 7) & 7u)) << 4) | (byte_in_row & 15u);
+}
+
 // chunk producer arguments (gram.cu)
 struct ProdParams {
     const float* A;   // (n1, rowsA, DP) points or increments of X   (rows i)
@@ -25,6 +66,9 @@ struct ProdParams {
     int diag;          // 1: buffer is [rows][n][P] holding only pairs (i, i), i in [i0, i0+ni)
     KernParams kp;
     float* out;
+    // stream layout (stream != 0): see StreamGeom
+    int stream, NW, njg;
+    long long SR;
 };
 
 int launch_delta_producer(int kind, const ProdParams& p, int DP, bool diff2d, cudaStream_t st);
@@ -38,6 +82,10 @@ int fo_lanes_per_pair(int ncols);
 int launch_sigkern_fo(const float* M, int n1, int Lrows, int n2, int ncols, int pitch, long long si, long long ss,
                       long long sj, int nlev, int difference, int upper_only, int i_off, int j_off, long long ldo,
                       long long lvl_stride, float* out, cudaStream_t st, int force_generic);
+// First-order recursion over a chunk in stream layout (sigstream.cu); items enumerate (i, jg) of an n1 x n2 pair block.
+int launch_sigkern_stream(const float* buf, const StreamGeom& g, long long nitems, int n1, int n2, int rows, int LP, int nlev,
+                          int upper_only, int i_off, int j_off, long long ldo, long long lvl_stride, float* out,
+                          cudaStream_t st);
 // Higher-order recursion (signature_algs.py:37-74), same addressing.
 int launch_sigkern_ho(const float* M, int n1, int Lrows, int n2, int ncols, long long si, long long ss, long long sj,
                       int nlev, int order, int difference, int upper_only, int i_off, int j_off, long long ldo,

@@ -71,7 +71,7 @@ struct SeqPlan {
     int rowsA, rowsB;       // rows of the prepared A / B arrays per sequence
     int out_rows, ncols;    // increment tile size
     int LP, P, G;
-    bool fast;              // TMA recursion eligible
+    bool fast;              // stream-fed recursion eligible (P = 16 LP <= 512 columns)
     size_t bytesA, bytesB, bytesAn, bytesBn, fixed;
 };
 
@@ -111,10 +111,15 @@ extern "C" size_t gpsig_seq_kern_workspace_bytes(int n1, int L1, int n2, int L2,
     SeqPlan pl;
     // worst case over kinds/difference: points (L rows) -- a few MB, the chunk buffer dominates
     if (make_plan(GPSIG_KERN_RBF, L1, L2, d, n1, n2, false, 0, pl) != GPSIG_OK) return 0;
-    const size_t row_bytes = (size_t)pl.out_rows * n2 * pl.P * 4;  // one row block of i
+    size_t row_bytes = (size_t)pl.out_rows * n2 * pl.P * 4;  // one row block of i
+    size_t all = row_bytes * (size_t)n1;
+    if (pl.fast) {  // stream layout: whole streams of skewed rows
+        const long long njg = (n2 + pl.G - 1) / pl.G;
+        row_bytes = stream_bytes(stream_geometry(njg, pl.out_rows, pl.LP));
+        all = stream_bytes(stream_geometry(njg * n1, pl.out_rows, pl.LP));
+    }
     size_t chunk = budget_bytes > pl.fixed ? budget_bytes - pl.fixed : 0;
     if (chunk < row_bytes) chunk = row_bytes;
-    const size_t all = row_bytes * (size_t)n1;
     if (chunk > all) chunk = all;
     return pl.fixed + align_up(chunk, 1024) + 1024;
 }
@@ -166,15 +171,37 @@ extern "C" int gpsig_seq_kern_levels(int kind, const float* params, const float*
     }
     const bool use_ho = order > 1;
     const bool upper = symmetric;
+    const bool use_stream = pl.fast && !use_ho && num_levels <= 8;
     int i0 = row_begin;
     while (i0 < row_end) {
         const int j_off = upper ? (i0 / pl.G) * pl.G : 0;
         const int nj = n2 - j_off;
-        const size_t row_bytes = (size_t)pl.out_rows * nj * pl.P * 4;
-        long long ib = (long long)(chunk_bytes / row_bytes);
-        if (ib < 1) return fail(GPSIG_E_WORKSPACE, "workspace too small for one row block: need %zu more bytes",
-                                row_bytes - chunk_bytes);
-        if (ib > row_end - i0) ib = row_end - i0;
+        const int njg = (nj + pl.G - 1) / pl.G;
+        long long ib = 0, nitems = 0;
+        StreamGeom geom{};
+        if (use_stream) {
+            // largest row block whose stream buffer fits the workspace (items grow monotonically with the block)
+            auto geom_for = [&](long long rows_i) {
+                return stream_geometry(items_before((int)rows_i, njg, pl.G, upper ? 1 : 0, i0, j_off), pl.out_rows, pl.LP);
+            };
+            if (stream_bytes(geom_for(1)) > chunk_bytes)
+                return fail(GPSIG_E_WORKSPACE, "workspace too small for one row block: need %zu more bytes",
+                            stream_bytes(geom_for(1)) - chunk_bytes);
+            long long lo = 1, hi = row_end - i0;
+            while (lo < hi) {
+                const long long mid = (lo + hi + 1) >> 1;
+                if (stream_bytes(geom_for(mid)) <= chunk_bytes) lo = mid; else hi = mid - 1;
+            }
+            ib = lo;
+            nitems = items_before((int)ib, njg, pl.G, upper ? 1 : 0, i0, j_off);
+            geom = geom_for(ib);
+        } else {
+            const size_t row_bytes = (size_t)pl.out_rows * nj * pl.P * 4;
+            ib = (long long)(chunk_bytes / row_bytes);
+            if (ib < 1) return fail(GPSIG_E_WORKSPACE, "workspace too small for one row block: need %zu more bytes",
+                                    row_bytes - chunk_bytes);
+            if (ib > row_end - i0) ib = row_end - i0;
+        }
         ProdParams pp;
         pp.A = A; pp.B = B; pp.An = An; pp.Bn = Bn;
         pp.rowsA = pl.rowsA; pp.rowsB = pl.rowsB;
@@ -183,15 +210,19 @@ extern "C" int gpsig_seq_kern_levels(int kind, const float* params, const float*
         pp.upper_only = upper ? 1 : 0; pp.G = pl.G; pp.diag = 0;
         pp.kp = make_kern_params(kind, params);
         pp.out = chunk;
+        pp.stream = use_stream ? 1 : 0; pp.NW = geom.NW; pp.SR = geom.SR; pp.njg = njg;
         rc = launch_delta_producer(kind, pp, pl.DP, pl.diff2d, st);
         if (rc) return rc;
         const long long ss = (long long)nj * pl.P, sj = pl.P, si = (long long)pl.out_rows * ss;
-        if (use_ho)
+        if (use_stream)
+            rc = launch_sigkern_stream(chunk, geom, nitems, (int)ib, nj, pl.out_rows, pl.LP, num_levels, upper ? 1 : 0, i0, j_off,
+                                       n2, per_level, out_base, st);
+        else if (use_ho)
             rc = launch_sigkern_ho(chunk, (int)ib, pl.out_rows, nj, pl.ncols, si, ss, sj, num_levels, order, 0, upper ? 1 : 0, i0,
                                    j_off, n2, per_level, out_base, st);
         else
             rc = launch_sigkern_fo(chunk, (int)ib, pl.out_rows, nj, pl.ncols, pl.P, si, ss, sj, num_levels, 0, upper ? 1 : 0, i0,
-                                   j_off, n2, per_level, out_base, st, pl.fast ? 0 : 1);
+                                   j_off, n2, per_level, out_base, st, 1);
         if (rc) return rc;
         i0 += (int)ib;
     }
@@ -226,13 +257,30 @@ extern "C" int gpsig_seq_kern_diag_levels(int kind, const float* params, const f
     float* chunk = (float*)w;
     if (workspace_bytes < (size_t)(w - (uint8_t*)workspace)) return fail(GPSIG_E_WORKSPACE, "workspace too small");
     const size_t chunk_bytes = workspace_bytes - (size_t)(w - (uint8_t*)workspace);
-    const size_t pair_bytes = (size_t)pl.out_rows * pl.P * 4;
-    long long cap = (long long)(chunk_bytes / pair_bytes);
-    if (cap < 1) return fail(GPSIG_E_WORKSPACE, "workspace too small for one diagonal tile");
+    const bool use_stream = pl.fast && order == 1 && num_levels <= 8;
+    long long cap;
+    if (use_stream) {
+        // pairs per launch: whole groups of G, largest count whose stream buffer fits
+        auto bytes_for = [&](long long pairs) { return stream_bytes(stream_geometry((pairs + pl.G - 1) / pl.G, pl.out_rows, pl.LP)); };
+        if (bytes_for(1) > chunk_bytes) return fail(GPSIG_E_WORKSPACE, "workspace too small for one diagonal tile");
+        long long lo = 1, hi = n;
+        while (lo < hi) {
+            const long long mid = (lo + hi + 1) >> 1;
+            if (bytes_for(mid) <= chunk_bytes) lo = mid; else hi = mid - 1;
+        }
+        cap = lo < n ? (lo / pl.G) * pl.G : lo;
+        if (cap < 1) return fail(GPSIG_E_WORKSPACE, "workspace too small for one diagonal pair group");
+    } else {
+        const size_t pair_bytes = (size_t)pl.out_rows * pl.P * 4;
+        cap = (long long)(chunk_bytes / pair_bytes);
+        if (cap < 1) return fail(GPSIG_E_WORKSPACE, "workspace too small for one diagonal tile");
+    }
     rc = launch_prep_points(X, n, L, d, inv_lengthscales, pl.lin_incr ? 1 : 0, pl.DP, A, An, st);
     if (rc) return rc;
     for (int e0 = 0; e0 < n; e0 += (int)cap) {
         const int ne = (int)((long long)(n - e0) < cap ? (n - e0) : cap);
+        const long long nitems = (ne + pl.G - 1) / pl.G;
+        const StreamGeom geom = stream_geometry(nitems, pl.out_rows, pl.LP);
         ProdParams pp;
         pp.A = A; pp.B = A; pp.An = An; pp.Bn = An;
         pp.rowsA = pl.rowsA; pp.rowsB = pl.rowsB;
@@ -241,16 +289,19 @@ extern "C" int gpsig_seq_kern_diag_levels(int kind, const float* params, const f
         pp.upper_only = 0; pp.G = pl.G; pp.diag = 1;
         pp.kp = make_kern_params(kind, params);
         pp.out = chunk;
+        pp.stream = use_stream ? 1 : 0; pp.NW = geom.NW; pp.SR = geom.SR; pp.njg = (int)nitems;
         rc = launch_delta_producer(kind, pp, pl.DP, pl.diff2d, st);
         if (rc) return rc;
-        // buffer [rows][ne][P]: one "row" of pairs, pair e at column e
+        // one "row" of pairs, pair e at column e
         const long long ss = (long long)ne * pl.P, sj = pl.P, si = (long long)pl.out_rows * ss;
-        if (order > 1)
+        if (use_stream)
+            rc = launch_sigkern_stream(chunk, geom, nitems, 1, ne, pl.out_rows, pl.LP, num_levels, 0, 0, e0, n, n, out_levels, st);
+        else if (order > 1)
             rc = launch_sigkern_ho(chunk, 1, pl.out_rows, ne, pl.ncols, si, ss, sj, num_levels, order, 0, 0, 0, e0, n, n,
                                    out_levels, st);
         else
             rc = launch_sigkern_fo(chunk, 1, pl.out_rows, ne, pl.ncols, pl.P, si, ss, sj, num_levels, 0, 0, 0, e0, n, n,
-                                   out_levels, st, pl.fast ? 0 : 1);
+                                   out_levels, st, 1);
         if (rc) return rc;
     }
     return GPSIG_OK;

@@ -44,19 +44,6 @@ struct FoParams {
     long long out_level_stride;
 };
 
-// sum_{x < i} floor(x / G)
-__host__ __device__ inline long long tri_floor(long long i, int G) {
-    long long b = i / G, r = i % G;
-    return (long long)G * b * (b - 1) / 2 + r * b;
-}
-// number of items in local rows < il.  With upper_only, local row il keeps the groups whose GLOBAL group index is
-// >= floor((i_off + il) / G); the chunk starts at global group j_off / G.
-__host__ __device__ inline long long items_before(int il, int njg, int G, int upper_only, int i_off, int j_off) {
-    if (!upper_only) return (long long)il * njg;
-    long long skipped = tri_floor((long long)i_off + il, G) - tri_floor(i_off, G) - (long long)il * (j_off / G);
-    return (long long)il * njg - skipped;
-}
-
 // item index -> (i, jg).  With upper_only, row i only has the groups jg >= i / G.
 __device__ __forceinline__ void decode_item(const FoParams& p, long long u, int& i, int& jg) {
     if (!p.upper_only) {
