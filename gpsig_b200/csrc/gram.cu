@@ -40,24 +40,39 @@ __device__ __forceinline__ float kern_eval(float dot, float sq, float xx, float 
 }
 
 // ---- prep: out[n, r, 0..DP) = scaled points (mode 0) or scaled time increments (mode 1), zero padded to DP --------
+//      mode 2 (RBF fast path): xh = (x - centre) / lengthscale * sqrt(log2 e), then (xh, -|xh|^2/2, 1, 0...) so that
+//      log2 k(x, y) = <xh, yh> - |xh|^2/2 - |yh|^2/2 is ONE dot product of the augmented vectors (the reader swaps the
+//      two extra components on the y side).  `centre` (d floats, may be NULL) only improves conditioning: the RBF
+//      kernel is translation invariant (kernels.py:765-776, :862-864).
 __global__ void prep_points_kernel(const float* __restrict__ X, long long n, int L, int d, const float* __restrict__ inv_ls,
-                                   int increments, int DP, float* __restrict__ out, float* __restrict__ norms) {
+                                   int mode, int DP, float* __restrict__ out, float* __restrict__ norms,
+                                   const float* __restrict__ centre) {
+    const int increments = mode == 1;
     const int Lo = increments ? L - 1 : L;
     const long long total = n * (long long)Lo;
+    const float rs = mode == 2 ? 1.2011224087864498f : 1.f;  // sqrt(log2 e)
+    const int nd = mode == 2 ? DP - 4 : DP;                  // feature slots
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const long long seq = idx / Lo;
         const int r = (int)(idx - seq * Lo);
         const float* x0 = X + (seq * L + r) * d;
         float nn = 0.f;
-        for (int c = 0; c < DP; ++c) {
+        for (int c = 0; c < nd; ++c) {
             float v = 0.f;
             if (c < d) {
-                const float s = inv_ls ? inv_ls[c] : 1.f;
-                v = increments ? (x0[d + c] - x0[c]) * s : x0[c] * s;
+                const float s = (inv_ls ? inv_ls[c] : 1.f) * rs;
+                const float x = (mode == 2 && centre) ? x0[c] - centre[c] : x0[c];
+                v = increments ? (x0[d + c] - x0[c]) * s : x * s;
             }
             out[idx * DP + c] = v;
             nn = fmaf(v, v, nn);
+        }
+        if (mode == 2) {
+            out[idx * DP + nd] = -0.5f * nn;
+            out[idx * DP + nd + 1] = 1.f;
+            out[idx * DP + nd + 2] = 0.f;
+            out[idx * DP + nd + 3] = 0.f;
         }
         if (norms) norms[idx] = nn;
     }
@@ -165,6 +180,162 @@ __global__ void __launch_bounds__(256) delta_producer_kernel(const ProdParams p)
     }
 }
 
+// ---- fast producer for the two headline static kernels -------------------------------------------------------------
+// LINEAR (RBF = false): A / B are time increments, out = <dx_s, dy_t>.          DPA = padded d.
+// RBF    (RBF = true) : A / B are augmented points (prep mode 2), f = 2^<x', y'>, out = 2-D increment of f.
+// Same thread mapping, skip logic and output addressing as delta_producer_kernel; the dot products run on packed
+// fma.rn.f32x2 (two features per instruction, sm_100), the exponential is one ex2.approx.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <bool RBF, int DPA>
+__global__ void __launch_bounds__(256) delta_producer_fast_kernel(const ProdParams p) {
+    extern __shared__ __align__(16) float sA[];  // [rowsA][DPA] of the current row sequence
+    constexpr int H = DPA / 2;
+    constexpr int NPT = RBF ? 5 : 4;
+    const int tpp = p.P >> 2;      // threads per pair row
+    const int ppb = blockDim.x / tpp;
+    const int jl = blockIdx.x * ppb + threadIdx.x / tpp;  // local pair column
+    const int t0 = (threadIdx.x % tpp) * 4;
+    const bool active = jl < p.nj;
+    const int j = p.j0 + (active ? jl : p.nj - 1);
+    const bool direct5 = RBF && (threadIdx.x % tpp == tpp - 1) && (t0 + 4 < p.rowsB) && (t0 + 3 < p.ncols);
+    // warp-uniform: does any lane of this warp have to evaluate its halo column itself?  (never when P == rowsB)
+    const bool any5 = RBF && __any_sync(0xffffffffu, direct5);
+    float2 y[NPT][H];
+#pragma unroll
+    for (int u = 0; u < NPT; ++u) {
+        const int t = t0 + u;
+        const bool ok = t < p.rowsB && (u < 4 || direct5);
+        const float2* src = reinterpret_cast<const float2*>(p.B + ((long long)j * p.rowsB + (ok ? t : 0)) * DPA);
+#pragma unroll
+        for (int h = 0; h < H; ++h) y[u][h] = ok ? src[h] : make_float2(0.f, 0.f);
+        if (RBF) {  // y side of the augmented product: (..., 1, -|y|^2/2)
+            const float2 a = y[u][H - 2];
+            y[u][H - 2] = make_float2(a.y, a.x);
+        }
+    }
+    const int group_last_j = (j / p.G) * p.G + p.G - 1;
+    const int ii_begin = p.diag ? jl : blockIdx.y, ii_end = p.diag ? jl + 1 : p.ni, ii_step = p.diag ? 1 : gridDim.y;
+    for (int ii = ii_begin; ii < ii_end; ii += ii_step) {
+        const int i = p.i0 + ii;
+        __syncthreads();
+        {
+            const float4* srcA = reinterpret_cast<const float4*>(p.A + (long long)i * p.rowsA * DPA);
+            float4* dstA = reinterpret_cast<float4*>(sA);
+            for (int e = threadIdx.x; e < p.rowsA * (DPA / 4); e += blockDim.x) dstA[e] = srcA[e];
+        }
+        __syncthreads();
+        if (!p.diag && p.upper_only && group_last_j < i) continue;
+        float* orow = p.diag ? p.out + (long long)jl * p.P + t0
+                             : p.out + (((long long)ii * p.out_rows) * p.nj + jl) * p.P + t0;
+        long long row_stride = (long long)p.nj * p.P;
+        if (p.stream) {
+            const int jgl = jl / p.G, q = jl - jgl * p.G;
+            const long long u = p.diag ? (long long)jgl
+                                       : items_before(ii, p.njg, p.G, p.upper_only, p.i0, p.j0) + jgl -
+                                             first_group(ii, p.G, p.upper_only, p.i0, p.j0);
+            const long long w = u % p.NW, n = u / p.NW;
+            const uint32_t sw = swizzle_in_row((uint32_t)(q * p.P + t0) * 4u);
+            orow = p.out + (w * p.SR + n * p.out_rows + (t0 >> 4)) * kSkewRowFloats + (sw >> 2);
+            row_stride = kSkewRowFloats;
+        }
+        float fprev[NPT];
+#pragma unroll
+        for (int u = 0; u < NPT; ++u) fprev[u] = 0.f;
+        for (int s = 0; s < p.rowsA; ++s) {
+            float2 x[H];
+            {
+                const float4* xs = reinterpret_cast<const float4*>(sA + s * DPA);
+#pragma unroll
+                for (int h4 = 0; h4 < DPA / 4; ++h4) {
+                    const float4 v = xs[h4];
+                    x[2 * h4] = make_float2(v.x, v.y);
+                    x[2 * h4 + 1] = make_float2(v.z, v.w);
+                }
+            }
+            float f[NPT];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int h = 0; h < H; ++h) acc = __ffma2_rn(x[h], y[u][h], acc);
+                const float v = acc.x + acc.y;
+                f[u] = RBF ? ex2_approx(v) : v;
+            }
+            if (RBF) {
+                f[NPT - 1] = __shfl_down_sync(0xffffffffu, f[0], 1);
+                if (any5) {  // uniform branch
+                    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int h = 0; h < H; ++h) acc = __ffma2_rn(x[h], y[NPT - 1][h], acc);
+                    const float v = ex2_approx(acc.x + acc.y);
+                    if (direct5) f[NPT - 1] = v;
+                }
+                if (s > 0 && active) {
+                    float4 o;
+                    o.x = (t0 + 0 < p.ncols) ? (f[1] - f[0]) - (fprev[1] - fprev[0]) : 0.f;
+                    o.y = (t0 + 1 < p.ncols) ? (f[2] - f[1]) - (fprev[2] - fprev[1]) : 0.f;
+                    o.z = (t0 + 2 < p.ncols) ? (f[3] - f[2]) - (fprev[3] - fprev[2]) : 0.f;
+                    o.w = (t0 + 3 < p.ncols) ? (f[NPT - 1] - f[3]) - (fprev[NPT - 1] - fprev[3]) : 0.f;
+                    *reinterpret_cast<float4*>(orow + (long long)(s - 1) * row_stride) = o;
+                }
+#pragma unroll
+                for (int u = 0; u < NPT; ++u) fprev[u] = f[u];
+            } else if (active) {
+                float4 o;
+                o.x = (t0 + 0 < p.ncols) ? f[0] : 0.f;
+                o.y = (t0 + 1 < p.ncols) ? f[1] : 0.f;
+                o.z = (t0 + 2 < p.ncols) ? f[2] : 0.f;
+                o.w = (t0 + 3 < p.ncols) ? f[3] : 0.f;
+                *reinterpret_cast<float4*>(orow + (long long)s * row_stride) = o;
+            }
+        }
+    }
+}
+
+template <bool RBF, int DPA>
+static int launch_producer_fast_dpa(const ProdParams& p, cudaStream_t st) {
+    const int tpp = p.P >> 2;
+    const int threads = p.diag ? tpp : 256;
+    const int ppb = threads / tpp;
+    const int gx = (p.nj + ppb - 1) / ppb;
+    int gy = p.diag ? 1 : p.ni;
+    const int target = num_sms() * 8;
+    if ((long long)gx * gy > target) gy = (target + gx - 1) / gx;
+    if (gy < 1) gy = 1;
+    if (gy > p.ni) gy = p.ni;
+    const size_t smem = (size_t)p.rowsA * DPA * sizeof(float);
+    auto k = delta_producer_fast_kernel<RBF, DPA>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<dim3(gx, gy), threads, smem, st>>>(p);
+    return check_launch();
+}
+
+// DPA: floats per prepared point.  Returns GPSIG_E_UNSUPPORTED when the shape has no fast instantiation.
+int launch_delta_producer_fast(bool rbf, const ProdParams& p, int DPA, cudaStream_t st) {
+    ProfScope prof(GPSIG_PROF_PRODUCER, st, p.diag ? (double)p.nj : (double)p.ni * p.nj);
+    if (rbf) {
+        switch (DPA) {
+            case 8: return launch_producer_fast_dpa<true, 8>(p, st);
+            case 12: return launch_producer_fast_dpa<true, 12>(p, st);
+            case 16: return launch_producer_fast_dpa<true, 16>(p, st);
+            case 20: return launch_producer_fast_dpa<true, 20>(p, st);
+        }
+    } else {
+        switch (DPA) {
+            case 4: return launch_producer_fast_dpa<false, 4>(p, st);
+            case 8: return launch_producer_fast_dpa<false, 8>(p, st);
+            case 12: return launch_producer_fast_dpa<false, 12>(p, st);
+            case 16: return launch_producer_fast_dpa<false, 16>(p, st);
+        }
+    }
+    return fail(GPSIG_E_UNSUPPORTED, "no fast producer for padded dimension %d", DPA);
+}
+
 template <int KIND, int DP>
 static int launch_producer_dp(const ProdParams& p, bool diff2d, cudaStream_t st) {
     const int tpp = p.P >> 2;          // P <= 512 -> at most 128 threads per pair row
@@ -218,14 +389,14 @@ int launch_delta_producer(int kind, const ProdParams& p, int DP, bool diff2d, cu
     return fail(GPSIG_E_BADARG, "unknown static kernel kind %d", kind);
 }
 
-int launch_prep_points(const float* X, long long n, int L, int d, const float* inv_ls, int increments, int DP, float* out,
-                       float* norms, cudaStream_t st) {
-    const long long total = n * (long long)(increments ? L - 1 : L);
+int launch_prep_points(const float* X, long long n, int L, int d, const float* inv_ls, int mode, int DP, float* out,
+                       float* norms, cudaStream_t st, const float* centre) {
+    const long long total = n * (long long)(mode == 1 ? L - 1 : L);
     if (total <= 0) return GPSIG_OK;
     ProfScope prof(GPSIG_PROF_PREP, st, (double)n);
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)num_sms() * 16;
-    prep_points_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(X, n, L, d, inv_ls, increments, DP, out, norms);
+    prep_points_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(X, n, L, d, inv_ls, mode, DP, out, norms, centre);
     return check_launch();
 }
 

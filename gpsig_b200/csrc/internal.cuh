@@ -72,8 +72,11 @@ struct ProdParams {
 };
 
 int launch_delta_producer(int kind, const ProdParams& p, int DP, bool diff2d, cudaStream_t st);
-int launch_prep_points(const float* X, long long n, int L, int d, const float* inv_ls, int increments, int DP, float* out,
-                       float* norms, cudaStream_t st);
+// fast producers (LINEAR on increments, RBF on augmented points); DPA = floats per prepared point
+int launch_delta_producer_fast(bool rbf, const ProdParams& p, int DPA, cudaStream_t st);
+// mode 0: scaled points, 1: scaled time increments, 2: RBF-augmented centred points (DP includes the 4 extra slots)
+int launch_prep_points(const float* X, long long n, int L, int d, const float* inv_ls, int mode, int DP, float* out,
+                       float* norms, cudaStream_t st, const float* centre = nullptr);
 KernParams make_kern_params(int kind, const float* params);
 
 int fo_lanes_per_pair(int ncols);

@@ -65,7 +65,9 @@ static int grid_for(long long total, int threads) {
 
 // ---- shapes of one pipeline run -------------------------------------------------------------------------------------
 struct SeqPlan {
-    int DP;                 // padded state-space dimension
+    int DP;                 // floats per prepared point (padded state-space dimension, +4 for the augmented RBF form)
+    int prep_mode;          // launch_prep_points mode
+    bool fast_prod;         // packed-FMA producer (LINEAR with increments, RBF)
     bool lin_incr;          // linear + difference: produce <dx, dy> directly
     bool diff2d;            // producer differences the point Gram in both time directions
     int rowsA, rowsB;       // rows of the prepared A / B arrays per sequence
@@ -79,6 +81,14 @@ static int make_plan(int kind, int L1, int L2, int d, int n1, int n2, bool symme
     pl.DP = (d + 3) / 4 * 4;
     pl.lin_incr = (kind == GPSIG_KERN_LINEAR) && difference;
     pl.diff2d = difference && !pl.lin_incr;
+    pl.prep_mode = pl.lin_incr ? 1 : 0;
+    pl.fast_prod = false;
+    if (pl.lin_incr && pl.DP <= 16) pl.fast_prod = true;
+    if (kind == GPSIG_KERN_RBF && difference && pl.DP <= 16) {
+        pl.fast_prod = true;
+        pl.prep_mode = 2;
+        pl.DP += 4;
+    }
     pl.rowsA = pl.lin_incr ? L1 - 1 : L1;
     pl.rowsB = pl.lin_incr ? L2 - 1 : L2;
     pl.out_rows = difference ? L1 - 1 : L1;
@@ -111,6 +121,10 @@ extern "C" size_t gpsig_seq_kern_workspace_bytes(int n1, int L1, int n2, int L2,
     SeqPlan pl;
     // worst case over kinds/difference: points (L rows) -- a few MB, the chunk buffer dominates
     if (make_plan(GPSIG_KERN_RBF, L1, L2, d, n1, n2, false, 0, pl) != GPSIG_OK) return 0;
+    {
+        SeqPlan pd;  // the augmented RBF form stores 4 more floats per point
+        if (make_plan(GPSIG_KERN_RBF, L1, L2, d, n1, n2, false, 1, pd) == GPSIG_OK && pd.fixed > pl.fixed) pl.fixed = pd.fixed;
+    }
     size_t row_bytes = (size_t)pl.out_rows * n2 * pl.P * 4;  // one row block of i
     size_t all = row_bytes * (size_t)n1;
     if (pl.fast) {  // stream layout: whole streams of skewed rows
@@ -163,10 +177,10 @@ extern "C" int gpsig_seq_kern_levels(int kind, const float* params, const float*
     float* chunk = (float*)w;
     const size_t chunk_bytes = workspace_bytes - (size_t)(w - (uint8_t*)workspace);
 
-    rc = launch_prep_points(X, n1, L1, d, inv_lengthscales, pl.lin_incr ? 1 : 0, pl.DP, A, An, st);
+    rc = launch_prep_points(X, n1, L1, d, inv_lengthscales, pl.prep_mode, pl.DP, A, An, st, X);
     if (rc) return rc;
     if (!symmetric) {
-        rc = launch_prep_points(X2, n2, L2, d, inv_lengthscales, pl.lin_incr ? 1 : 0, pl.DP, B, Bn, st);
+        rc = launch_prep_points(X2, n2, L2, d, inv_lengthscales, pl.prep_mode, pl.DP, B, Bn, st, X);
         if (rc) return rc;
     }
     const bool use_ho = order > 1;
@@ -211,7 +225,8 @@ extern "C" int gpsig_seq_kern_levels(int kind, const float* params, const float*
         pp.kp = make_kern_params(kind, params);
         pp.out = chunk;
         pp.stream = use_stream ? 1 : 0; pp.NW = geom.NW; pp.SR = geom.SR; pp.njg = njg;
-        rc = launch_delta_producer(kind, pp, pl.DP, pl.diff2d, st);
+        rc = pl.fast_prod ? launch_delta_producer_fast(kind == GPSIG_KERN_RBF, pp, pl.DP, st)
+                          : launch_delta_producer(kind, pp, pl.DP, pl.diff2d, st);
         if (rc) return rc;
         const long long ss = (long long)nj * pl.P, sj = pl.P, si = (long long)pl.out_rows * ss;
         if (use_stream)
@@ -275,7 +290,7 @@ extern "C" int gpsig_seq_kern_diag_levels(int kind, const float* params, const f
         cap = (long long)(chunk_bytes / pair_bytes);
         if (cap < 1) return fail(GPSIG_E_WORKSPACE, "workspace too small for one diagonal tile");
     }
-    rc = launch_prep_points(X, n, L, d, inv_lengthscales, pl.lin_incr ? 1 : 0, pl.DP, A, An, st);
+    rc = launch_prep_points(X, n, L, d, inv_lengthscales, pl.prep_mode, pl.DP, A, An, st, X);
     if (rc) return rc;
     for (int e0 = 0; e0 < n; e0 += (int)cap) {
         const int ne = (int)((long long)(n - e0) < cap ? (n - e0) : cap);
@@ -290,7 +305,8 @@ extern "C" int gpsig_seq_kern_diag_levels(int kind, const float* params, const f
         pp.kp = make_kern_params(kind, params);
         pp.out = chunk;
         pp.stream = use_stream ? 1 : 0; pp.NW = geom.NW; pp.SR = geom.SR; pp.njg = (int)nitems;
-        rc = launch_delta_producer(kind, pp, pl.DP, pl.diff2d, st);
+        rc = pl.fast_prod ? launch_delta_producer_fast(kind == GPSIG_KERN_RBF, pp, pl.DP, st)
+                          : launch_delta_producer(kind, pp, pl.DP, pl.diff2d, st);
         if (rc) return rc;
         // one "row" of pairs, pair e at column e
         const long long ss = (long long)ne * pl.P, sj = pl.P, si = (long long)pl.out_rows * ss;
