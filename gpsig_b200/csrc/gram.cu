@@ -81,7 +81,7 @@ __global__ void prep_points_kernel(const float* __restrict__ X, long long n, int
 // ---- the chunk producer (ProdParams: internal.cuh) ----------------------------------------------------------------
 // One thread owns 4 consecutive columns t0..t0+3 of one pair column j and walks down the rows of the row block.
 // DIFF2D: out = (f[s+1][t+1] - f[s+1][t]) - (f[s][t+1] - f[s][t]); the value at t0+4 comes from the next lane by
-// shuffle (the last thread of a pair row evaluates it itself, and only when that column is a real increment).
+// shuffle (a thread whose right-hand neighbour is in another warp or another pair evaluates it itself, and only when that column is a real increment).
 // Skip decisions are warp-uniform (a warp never straddles two consumer pair groups), so full-mask shuffles are safe.
 template <int KIND, int DP, bool DIFF2D>
 __global__ void __launch_bounds__(256) delta_producer_kernel(const ProdParams p) {
@@ -93,7 +93,8 @@ __global__ void __launch_bounds__(256) delta_producer_kernel(const ProdParams p)
     const int t0 = (threadIdx.x % tpp) * 4;
     const bool active = jl < p.nj;
     const int j = p.j0 + (active ? jl : p.nj - 1);
-    const bool direct5 = DIFF2D && (threadIdx.x % tpp == tpp - 1) && (t0 + 4 < p.rowsB) && (t0 + 3 < p.ncols);
+    const bool direct5 = DIFF2D && ((threadIdx.x % tpp == tpp - 1) || (threadIdx.x & 31) == 31) && (t0 + 4 < p.rowsB) &&
+                         (t0 + 3 < p.ncols);  // the right-hand neighbour column is not held by the next lane of this warp
     constexpr int NPT = DIFF2D ? 5 : 4;
     float y[NPT][DP];
     float yn[NPT];
@@ -202,7 +203,8 @@ __global__ void __launch_bounds__(256) delta_producer_fast_kernel(const ProdPara
     const int t0 = (threadIdx.x % tpp) * 4;
     const bool active = jl < p.nj;
     const int j = p.j0 + (active ? jl : p.nj - 1);
-    const bool direct5 = RBF && (threadIdx.x % tpp == tpp - 1) && (t0 + 4 < p.rowsB) && (t0 + 3 < p.ncols);
+    const bool direct5 = RBF && ((threadIdx.x % tpp == tpp - 1) || (threadIdx.x & 31) == 31) && (t0 + 4 < p.rowsB) &&
+                         (t0 + 3 < p.ncols);  // the right-hand neighbour column is not held by the next lane of this warp
     // warp-uniform: does any lane of this warp have to evaluate its halo column itself?  (never when P == rowsB)
     const bool any5 = RBF && __any_sync(0xffffffffu, direct5);
     float2 y[NPT][H];

@@ -43,7 +43,7 @@ struct StreamGeom {
     int ncw;        // consumer warps per CTA
     int grid;
 };
-StreamGeom stream_geometry(long long nitems, int rows, int LP);
+StreamGeom stream_geometry(long long nitems, int rows, int LP, int nlev);
 inline size_t stream_bytes(const StreamGeom& g) { return (size_t)g.NW * (size_t)g.SR * 2048; }
 __host__ __device__ inline uint32_t swizzle_in_row(uint32_t byte_in_row) {
     return ((byte_in_row >> 7) << 7) | ((((byte_in_row >> 4) & 7u) ^ ((byte_in_row >> 7) & 7u)) << 4) | (byte_in_row & 15u);

@@ -6,6 +6,12 @@ namespace gpsig {
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// the stream geometry (consumer warps per CTA) depends on the number of levels: size workspaces for the larger one
+static size_t stream_bytes_worst(long long nitems, int rows, int LP) {
+    const size_t a = stream_bytes(stream_geometry(nitems, rows, LP, 5)), b = stream_bytes(stream_geometry(nitems, rows, LP, 8));
+    return a > b ? a : b;
+}
+
 // ---- small helper kernels -----------------------------------------------------------------------------------------
 __global__ void fill_levels_trivial_kernel(float* out, long long per_level, int nl) {
     // level 0 = 1, levels >= 1 = 0 (no increments at all: L == 1 with differencing)
@@ -129,8 +135,8 @@ extern "C" size_t gpsig_seq_kern_workspace_bytes(int n1, int L1, int n2, int L2,
     size_t all = row_bytes * (size_t)n1;
     if (pl.fast) {  // stream layout: whole streams of skewed rows
         const long long njg = (n2 + pl.G - 1) / pl.G;
-        row_bytes = stream_bytes(stream_geometry(njg, pl.out_rows, pl.LP));
-        all = stream_bytes(stream_geometry(njg * n1, pl.out_rows, pl.LP));
+        row_bytes = stream_bytes_worst(njg, pl.out_rows, pl.LP);
+        all = stream_bytes_worst(njg * n1, pl.out_rows, pl.LP);
     }
     size_t chunk = budget_bytes > pl.fixed ? budget_bytes - pl.fixed : 0;
     if (chunk < row_bytes) chunk = row_bytes;
@@ -196,7 +202,7 @@ extern "C" int gpsig_seq_kern_levels(int kind, const float* params, const float*
         if (use_stream) {
             // largest row block whose stream buffer fits the workspace (items grow monotonically with the block)
             auto geom_for = [&](long long rows_i) {
-                return stream_geometry(items_before((int)rows_i, njg, pl.G, upper ? 1 : 0, i0, j_off), pl.out_rows, pl.LP);
+                return stream_geometry(items_before((int)rows_i, njg, pl.G, upper ? 1 : 0, i0, j_off), pl.out_rows, pl.LP, num_levels);
             };
             if (stream_bytes(geom_for(1)) > chunk_bytes)
                 return fail(GPSIG_E_WORKSPACE, "workspace too small for one row block: need %zu more bytes",
@@ -276,7 +282,7 @@ extern "C" int gpsig_seq_kern_diag_levels(int kind, const float* params, const f
     long long cap;
     if (use_stream) {
         // pairs per launch: whole groups of G, largest count whose stream buffer fits
-        auto bytes_for = [&](long long pairs) { return stream_bytes(stream_geometry((pairs + pl.G - 1) / pl.G, pl.out_rows, pl.LP)); };
+        auto bytes_for = [&](long long pairs) { return stream_bytes(stream_geometry((pairs + pl.G - 1) / pl.G, pl.out_rows, pl.LP, num_levels)); };
         if (bytes_for(1) > chunk_bytes) return fail(GPSIG_E_WORKSPACE, "workspace too small for one diagonal tile");
         long long lo = 1, hi = n;
         while (lo < hi) {
@@ -295,7 +301,7 @@ extern "C" int gpsig_seq_kern_diag_levels(int kind, const float* params, const f
     for (int e0 = 0; e0 < n; e0 += (int)cap) {
         const int ne = (int)((long long)(n - e0) < cap ? (n - e0) : cap);
         const long long nitems = (ne + pl.G - 1) / pl.G;
-        const StreamGeom geom = stream_geometry(nitems, pl.out_rows, pl.LP);
+        const StreamGeom geom = stream_geometry(nitems, pl.out_rows, pl.LP, num_levels);
         ProdParams pp;
         pp.A = A; pp.B = A; pp.An = An; pp.Bn = An;
         pp.rowsA = pl.rowsA; pp.rowsB = pl.rowsB;

@@ -7,7 +7,8 @@
 // rows per warp resident in shared memory.  Here the producer kernel has already applied the skew and the 128-byte
 // XOR swizzle in global memory, so
 //   * a consumer warp's input is ONE contiguous byte stream: the TMA producer warp fetches it with 1-D bulk copies of
-//     R = 4 skewed rows (8 KB) per instruction into a 3-stage ring per consumer (full/empty mbarriers);
+//     R = 4 skewed rows (8 KB) per instruction into a 2-stage ring per consumer (full/empty mbarriers); 11 consumer
+//     warps + 1 producer warp per SM up to 5 levels (168 registers), 7 + 1 for 6..8 levels (255 registers);
 //   * at step T all 32 lanes read skewed row T (conflict-free LDS.128), so a stage is dead after R steps and every
 //     byte of shared memory is prefetch depth;
 //   * the arithmetic is unchanged: lane l of a pair owns the 16-column strip l and keeps A_m[s, t] of all levels in
@@ -15,6 +16,8 @@
 //     one shfl.up per level per row;  A_m[r+1, t] = A_m[r, t] + p_m ;  p_m += Delta[r, t] * A_{m-1}[r, t].
 //   * row T + 1 is loaded into registers while row T is computed and the barrier of the next stage is probed one step
 //     before it is needed, so neither LDS nor mbarrier latency sits on the critical path.
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "internal.cuh"
@@ -66,8 +69,10 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <int NLEV>
-__global__ void __maxnreg__(224) sigkern_fo_stream_kernel(const StParams p) {
+// MAXW = warps the register budget is sized for (registers are allocated in groups of 4 warps: 12 warps -> 168
+// registers per thread, enough up to 5 levels; 8 warps -> 255 for 6..8 levels).  The launch may use fewer warps.
+template <int NLEV, int MAXW>
+__global__ void __launch_bounds__(MAXW * 32, 1) sigkern_fo_stream_kernel(const StParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int NA = NLEV > 1 ? NLEV - 1 : 1;
     const int ncw = (blockDim.x >> 5) - 1;  // consumer warps; warp 0 is the bulk-copy producer
@@ -235,12 +240,25 @@ static int ilog2_exact(int x) {
     return l;
 }
 
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
 // geometry of a launch over `nitems` items of `rows` increment rows each
-StreamGeom stream_geometry(long long nitems, int rows, int LP) {
+StreamGeom stream_geometry(long long nitems, int rows, int LP, int nlev) {
     StreamGeom g;
-    g.ncw = 8;
-    g.R = 4;
-    g.S = 3;
+    // consumer warps per CTA / rows per bulk copy / ring depth (GPSIG_STREAM_* are tuning knobs for experiments)
+    const int maxw = nlev <= 5 ? 12 : 8;
+    g.ncw = nlev <= 5 ? env_int("GPSIG_STREAM_NCW", 11) : 7;
+    if (g.ncw > maxw - 1) g.ncw = maxw - 1;
+    if (g.ncw < 1) g.ncw = 1;
+    g.R = env_int("GPSIG_STREAM_R", 4);
+    g.S = env_int("GPSIG_STREAM_S", nlev <= 5 ? 2 : 3);
+    if (g.R < 1) g.R = 1;
+    if (g.S < 2) g.S = 2;
+    while ((size_t)g.ncw * g.S * ((size_t)g.R * 2048 + 16) > 232448 && g.S > 2) --g.S;
+    while ((size_t)g.ncw * g.S * ((size_t)g.R * 2048 + 16) > 232448 && g.R > 1) --g.R;
     long long want = (nitems + g.ncw - 1) / g.ncw;
     g.grid = (int)(want < num_sms() ? want : num_sms());
     if (g.grid < 1) g.grid = 1;
@@ -253,7 +271,9 @@ StreamGeom stream_geometry(long long nitems, int rows, int LP) {
 
 template <int NLEV>
 static int launch_stream_inst(const StParams& p, const StreamGeom& g, size_t smem, cudaStream_t st) {
-    auto kern = sigkern_fo_stream_kernel<NLEV>;
+    constexpr int MAXW = NLEV <= 5 ? 12 : 8;
+    if (g.ncw + 1 > MAXW) return fail(GPSIG_E_BADARG, "stream geometry has too many warps for %d levels", NLEV);
+    auto kern = sigkern_fo_stream_kernel<NLEV, MAXW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     kern<<<g.grid, (g.ncw + 1) * 32, smem, st>>>(p);

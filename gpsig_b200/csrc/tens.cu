@@ -206,6 +206,198 @@ static int launch_tsf(const TsfParams& p, cudaStream_t st) {
     return check_launch();
 }
 
+
+// ---- fast fused tensor-vs-sequence kernel (first order, LINEAR / RBF) ----------------------------------------------
+// kernels.py:313-340 + signature_algs.py:101-127 without the (T, nz, n, L) Gram: one thread sweeps time for TWO
+// sequences against ONE inducing tensor whose T (x2) component points sit in shared memory (broadcast reads); the T
+// running prefixes of both sequences live in registers (everything is unrolled over the component index).
+//   LINEAR: h_k(t) = <dz_k, dx_t>        (dz = z^1 - z^0 with increments, dx = time increment: bilinearity of :330, :114)
+//   RBF   : v_k(t) = 2^<z'^1, x'> - 2^<z'^0, x'>  on the augmented points of prep mode 2;  h_k(t) = v_k(t) - v_k(t-1)
+// The dot products run on packed fma.rn.f32x2.
+__device__ __forceinline__ float tsf_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+struct TsfFastParams {
+    const float* Z;   // prepared tensor points (T, nz, ninc, DPA)
+    const float* X;   // prepared sequence points / increments (n, rowsX, DPA)
+    long long nz, n;
+    int rowsX;        // L (points) or L - 1 (increments)
+    int increments, difference;
+    float* out;       // (NLEV + 1, nz, n)
+};
+
+constexpr int kTsfZPerBlock = 8;   // warps per block, one inducing tensor each
+constexpr int kTsfSeqPerThread = 2;
+
+template <bool RBF, int NLEV, int DPA>
+__global__ void __launch_bounds__(kTsfZPerBlock * 32) tens_seq_fast_kernel(const TsfFastParams p) {
+    constexpr int T = NLEV * (NLEV + 1) / 2, H = DPA / 2, NS = kTsfSeqPerThread;
+    extern __shared__ __align__(16) float szf[];  // [warp][T][ninc'][DPA]; LINEAR stores dz (ninc' = 1)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ninc = p.increments ? 2 : 1;
+    const int nst = (RBF && p.increments) ? 2 : 1;  // points kept per component in shared memory
+    const long long z = (long long)blockIdx.y * kTsfZPerBlock + warp;
+    const bool zok = z < p.nz;
+    float* sz = szf + (size_t)warp * T * nst * DPA;
+    if (zok) {
+        for (int e = lane; e < T * nst * DPA; e += 32) {
+            const int k = e / (nst * DPA), r = e - k * nst * DPA, w = r / DPA, c = r - w * DPA;
+            const float* src = p.Z + (((long long)k * p.nz + z) * ninc) * DPA;
+            float v;
+            if (!RBF && p.increments) v = src[DPA + c] - src[c];  // dz
+            else v = src[w * DPA + c];
+            sz[e] = v;
+        }
+    }
+    __syncwarp();
+    long long nn[NS];
+    bool nok[NS];
+#pragma unroll
+    for (int a = 0; a < NS; ++a) {
+        nn[a] = ((long long)blockIdx.x * NS + a) * 32 + lane;
+        nok[a] = nn[a] < p.n;
+    }
+    if (!zok) return;
+    float c[NS][T], vprev[NS][T];
+#pragma unroll
+    for (int a = 0; a < NS; ++a)
+#pragma unroll
+        for (int k = 0; k < T; ++k) { c[a][k] = 0.f; vprev[a][k] = 0.f; }
+    const bool tdiff = RBF && p.difference;  // LINEAR takes its time difference from the prepared increments
+    for (int t = 0; t < p.rowsX; ++t) {
+        float2 x[NS][H];
+#pragma unroll
+        for (int a = 0; a < NS; ++a) {
+            const float4* xs = reinterpret_cast<const float4*>(p.X + ((nok[a] ? nn[a] : 0) * p.rowsX + t) * DPA);
+#pragma unroll
+            for (int h4 = 0; h4 < DPA / 4; ++h4) {
+                const float4 v = __ldg(xs + h4);
+                x[a][2 * h4] = make_float2(v.x, v.y);
+                x[a][2 * h4 + 1] = make_float2(v.z, v.w);
+            }
+            if (RBF) {  // sequence side of the augmented product: (..., 1, -|x|^2/2)
+                const float2 q = x[a][H - 2];
+                x[a][H - 2] = make_float2(q.y, q.x);
+            }
+        }
+        int k = 0;
+#pragma unroll
+        for (int m = 1; m <= NLEV; ++m) {
+            float prev_excl[NS];
+#pragma unroll
+            for (int a = 0; a < NS; ++a) prev_excl[a] = 0.f;
+#pragma unroll
+            for (int pi = 0; pi < m; ++pi, ++k) {
+                float v[NS];
+                if (RBF && nst == 2) {
+                    float2 z0[H], z1[H];
+                    const float4* zp = reinterpret_cast<const float4*>(sz + (k * 2) * DPA);
+#pragma unroll
+                    for (int h4 = 0; h4 < DPA / 4; ++h4) {
+                        const float4 u0 = zp[h4], u1 = zp[DPA / 4 + h4];
+                        z0[2 * h4] = make_float2(u0.x, u0.y); z0[2 * h4 + 1] = make_float2(u0.z, u0.w);
+                        z1[2 * h4] = make_float2(u1.x, u1.y); z1[2 * h4 + 1] = make_float2(u1.z, u1.w);
+                    }
+#pragma unroll
+                    for (int a = 0; a < NS; ++a) {
+                        float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int h = 0; h < H; ++h) { a0 = __ffma2_rn(z0[h], x[a][h], a0); a1 = __ffma2_rn(z1[h], x[a][h], a1); }
+                        v[a] = tsf_ex2(a1.x + a1.y) - tsf_ex2(a0.x + a0.y);
+                    }
+                } else {
+                    float2 z0[H];
+                    const float4* zp = reinterpret_cast<const float4*>(sz + k * DPA);
+#pragma unroll
+                    for (int h4 = 0; h4 < DPA / 4; ++h4) {
+                        const float4 u0 = zp[h4];
+                        z0[2 * h4] = make_float2(u0.x, u0.y); z0[2 * h4 + 1] = make_float2(u0.z, u0.w);
+                    }
+#pragma unroll
+                    for (int a = 0; a < NS; ++a) {
+                        float2 a0 = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int h = 0; h < H; ++h) a0 = __ffma2_rn(z0[h], x[a][h], a0);
+                        const float d0 = a0.x + a0.y;
+                        v[a] = RBF ? tsf_ex2(d0) : d0;
+                    }
+                }
+#pragma unroll
+                for (int a = 0; a < NS; ++a) {
+                    const float h = tdiff ? v[a] - vprev[a][k] : v[a];
+                    if (tdiff) vprev[a][k] = v[a];
+                    const float val = (tdiff && t == 0) ? 0.f : (pi == 0 ? h : h * prev_excl[a]);
+                    prev_excl[a] = c[a][k];
+                    c[a][k] += val;
+                }
+            }
+        }
+    }
+    const long long per = p.nz * p.n;
+#pragma unroll
+    for (int a = 0; a < NS; ++a) {
+        if (!nok[a]) continue;
+        const long long idx = z * p.n + nn[a];
+        p.out[idx] = 1.f;
+        int k0 = 0;
+#pragma unroll
+        for (int m = 1; m <= NLEV; ++m) {
+            p.out[(long long)m * per + idx] = c[a][k0 + m - 1];
+            k0 += m;
+        }
+    }
+}
+
+template <bool RBF, int NLEV, int DPA>
+static int launch_tsf_fast_inst(const TsfFastParams& p, cudaStream_t st) {
+    constexpr int T = NLEV * (NLEV + 1) / 2;
+    const int nst = (RBF && p.increments) ? 2 : 1;
+    const size_t smem = (size_t)kTsfZPerBlock * T * nst * DPA * sizeof(float);
+    dim3 grid((unsigned)((p.n + 32 * kTsfSeqPerThread - 1) / (32 * kTsfSeqPerThread)),
+              (unsigned)((p.nz + kTsfZPerBlock - 1) / kTsfZPerBlock));
+    ProfScope prof(GPSIG_PROF_TENS, st, (double)p.nz * p.n);
+    auto k = tens_seq_fast_kernel<RBF, NLEV, DPA>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<grid, kTsfZPerBlock * 32, smem, st>>>(p);
+    return check_launch();
+}
+
+template <bool RBF, int DPA>
+static int launch_tsf_fast_lev(int nlev, const TsfFastParams& p, cudaStream_t st) {
+    switch (nlev) {
+        case 1: return launch_tsf_fast_inst<RBF, 1, DPA>(p, st);
+        case 2: return launch_tsf_fast_inst<RBF, 2, DPA>(p, st);
+        case 3: return launch_tsf_fast_inst<RBF, 3, DPA>(p, st);
+        case 4: return launch_tsf_fast_inst<RBF, 4, DPA>(p, st);
+        case 5: return launch_tsf_fast_inst<RBF, 5, DPA>(p, st);
+        case 6: return launch_tsf_fast_inst<RBF, 6, DPA>(p, st);
+    }
+    return GPSIG_E_UNSUPPORTED;
+}
+
+// returns GPSIG_E_UNSUPPORTED (without an error detail) when there is no instantiation for the shape
+static int launch_tsf_fast(bool rbf, int nlev, int DPA, const TsfFastParams& p, cudaStream_t st) {
+    if (rbf) {
+        switch (DPA) {
+            case 8: return launch_tsf_fast_lev<true, 8>(nlev, p, st);
+            case 12: return launch_tsf_fast_lev<true, 12>(nlev, p, st);
+            case 16: return launch_tsf_fast_lev<true, 16>(nlev, p, st);
+            case 20: return launch_tsf_fast_lev<true, 20>(nlev, p, st);
+        }
+    } else {
+        switch (DPA) {
+            case 4: return launch_tsf_fast_lev<false, 4>(nlev, p, st);
+            case 8: return launch_tsf_fast_lev<false, 8>(nlev, p, st);
+            case 12: return launch_tsf_fast_lev<false, 12>(nlev, p, st);
+            case 16: return launch_tsf_fast_lev<false, 16>(nlev, p, st);
+        }
+    }
+    return GPSIG_E_UNSUPPORTED;
+}
+
 }  // namespace gpsig
 
 using namespace gpsig;
@@ -237,6 +429,20 @@ extern "C" int gpsig_tens_vs_seq_levels(const float* M, int num_levels, long nz,
     return check_launch();
 }
 
+// keep stream-ordered scratch allocations cached in the device's default pool instead of returning them to the driver
+// at every synchronisation (one attribute write per device, first call only)
+static void keep_pool_cached() {
+    static thread_local int done_dev = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev == done_dev) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done_dev = dev;
+}
+
 // Z: (T, nz, d) or (T, nz, 2, d) raw; X (n, L, d) raw.  Scaling and zero-padding to DP happen in a workspace that is
 // allocated stream-ordered (a few MB: (T nz ninc + n L) (DP + 1) floats) and released after the launch.
 extern "C" int gpsig_tens_seq_kern_levels(int kind, const float* params, const float* Z, long nz, int increments,
@@ -249,6 +455,31 @@ extern "C" int gpsig_tens_seq_kern_levels(int kind, const float* params, const f
     if (order < 1 || order > num_levels) return fail(GPSIG_E_BADARG, "order must be in [1, num_levels]");
     const int T = num_levels * (num_levels + 1) / 2, ninc = increments ? 2 : 1, DP = (d + 3) / 4 * 4;
     const long long zpts = (long long)T * nz * ninc, xpts = (long long)n * L;
+    keep_pool_cached();
+    // fast path: first order, LINEAR / RBF, up to 6 levels
+    const bool fast = order == 1 && num_levels <= 6 && DP <= 16 && (kind == GPSIG_KERN_LINEAR || kind == GPSIG_KERN_RBF) &&
+                      !(kind == GPSIG_KERN_LINEAR && difference && L < 2);
+    if (fast) {
+        const bool rbf = kind == GPSIG_KERN_RBF;
+        const int DPA = rbf ? DP + 4 : DP;
+        const int xmode = rbf ? 2 : (difference ? 1 : 0);
+        const int rowsX = xmode == 1 ? L - 1 : L;
+        float* fb = nullptr;
+        cudaError_t fe = cudaMallocAsync((void**)&fb, (size_t)(zpts + xpts) * DPA * sizeof(float), st);
+        if (fe != cudaSuccess) return (int)fe;
+        float* Zs = fb;
+        float* Xs = Zs + zpts * DPA;
+        int frc = launch_prep_points(Z, zpts, 1, d, inv_lengthscales, rbf ? 2 : 0, DPA, Zs, nullptr, st, X);
+        if (!frc) frc = launch_prep_points(X, n, L, d, inv_lengthscales, xmode, DPA, Xs, nullptr, st, X);
+        if (!frc) {
+            TsfFastParams fp;
+            fp.Z = Zs; fp.X = Xs; fp.nz = nz; fp.n = n; fp.rowsX = rowsX;
+            fp.increments = increments ? 1 : 0; fp.difference = difference ? 1 : 0; fp.out = out_levels;
+            frc = launch_tsf_fast(rbf, num_levels, DPA, fp, st);
+        }
+        cudaFreeAsync(fb, st);
+        if (frc != GPSIG_E_UNSUPPORTED) return frc;
+    }
     float* buf = nullptr;
     cudaError_t e = cudaMallocAsync((void**)&buf, (size_t)(zpts + xpts) * (DP + 1) * sizeof(float), st);
     if (e != cudaSuccess) return (int)e;

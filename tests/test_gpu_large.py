@@ -126,3 +126,41 @@ def test_svgp_elbo_vs_oracle():
         mu, var = m.predict_f(X)
         assert_close(mu.cpu().numpy(), fm, tol=2e-4, msg="fmean")
         assert_close(var.cpu().numpy(), fv, tol=2e-4, msg="fvar")
+
+
+@pytest.mark.parametrize("M", [6, 7, 8])
+@pytest.mark.parametrize("kind", ["linear", "rbf"])
+def test_many_levels_on_the_stream_path(kind, M):
+    """num_levels 6..8 use the 8-warp instantiation of the stream recursion (register budget); L=40 -> LP=4, G=8."""
+    X = random_walks(37, 40, 3, 20 + M).reshape(37, -1)
+    Y = random_walks(10, 40, 3, 40 + M).reshape(10, -1)
+    k, ko = _pair(kind, 40, 3, M, lengthscales=1.7)
+    assert_levels_close(k.K(X, return_levels=True).cpu().numpy(), ko.K(X, return_levels=True), msg="symm M=%d" % M)
+    assert_levels_close(k.K(X, Y, return_levels=True).cpu().numpy(), ko.K(X, Y, return_levels=True), msg="rect M=%d" % M)
+
+
+@pytest.mark.parametrize("L,d,M", [(100, 10, 6), (45, 3, 4), (17, 5, 2), (300, 2, 3), (2, 4, 3)])
+@pytest.mark.parametrize("kind", ["linear", "rbf"])
+def test_sequence_shapes_off_the_headline_tile(kind, L, d, M):
+    """config-5 tile (L=100, d=10, M=6), LIBRAS-like odd lengths, long sequences (LP=32), two-point sequences."""
+    n = 21
+    X = random_walks(n, L, d, L + d).reshape(n, -1)
+    k, ko = _pair(kind, L, d, M, lengthscales=0.5 * np.sqrt(d) + 0.5)
+    assert_levels_close(k.K(X, return_levels=True).cpu().numpy(), ko.K(X, return_levels=True, row_block=7), msg="symm")
+    k2, ko2 = _pair(kind, L, d, M, lengthscales=0.5 * np.sqrt(d) + 0.5, normalization=False)
+    assert_close(k2.Kdiag(X).cpu().numpy(), ko2.Kdiag(X), msg="Kdiag")
+
+
+@pytest.mark.parametrize("kind", ["linear", "rbf"])
+@pytest.mark.parametrize("L,d,M,diff", [(100, 10, 6, True), (33, 3, 4, True), (20, 5, 3, False), (64, 16, 2, True),
+                                        (12, 2, 7, True)])
+def test_kuf_fast_and_generic_paths_vs_oracle(kind, L, d, M, diff):
+    """fused tensor-vs-sequence kernel: fast instantiations (M <= 6, d <= 16) and the generic fallback (M = 7)."""
+    rng = np.random.default_rng(L * d + M)
+    n, nz, T = 45, 11, M * (M + 1) // 2
+    X = random_walks(n, L, d, 9).reshape(n, -1)
+    for inc in (False, True):
+        Z = 0.5 * rng.standard_normal((T, nz, 2, d) if inc else (T, nz, d))
+        k, ko = _pair(kind, L, d, M, lengthscales=1.3 * np.ones(d), difference=diff, normalization=False)
+        got = k.K_tens_vs_seq(Z, X, increments=inc, return_levels=True).cpu().numpy()
+        assert_levels_close(got, ko.K_tens_vs_seq(Z, X, increments=inc, return_levels=True), msg="Kuf %s inc=%s" % (kind, inc))
