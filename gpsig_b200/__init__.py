@@ -7,6 +7,7 @@ All arithmetic on the path runs in the CUDA library built from gpsig_b200/csrc (
 torch tensors are device containers.
 """
 from . import settings  # noqa: F401
+from . import low_rank_calculations  # noqa: F401
 from . import signature_algs  # noqa: F401
 from . import kernels  # noqa: F401
 from . import inducing_variables  # noqa: F401

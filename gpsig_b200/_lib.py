@@ -22,6 +22,8 @@ _PROTOTYPES = {
                                           ctypes.POINTER(ctypes.c_double)]),
     "gpsig_scale_features": (ctypes.c_int, [_c_float_p, ctypes.c_long, ctypes.c_int, _c_float_p, ctypes.c_int, _c_float_p,
                                             ctypes.c_void_p]),
+    "gpsig_add_lags": (ctypes.c_int, [_c_float_p, ctypes.c_long, ctypes.c_int, ctypes.c_int, _c_float_p, ctypes.c_int, _c_float_p,
+                                      ctypes.c_void_p]),
     "gpsig_gram": (ctypes.c_int, [ctypes.c_int, _c_float_p, ctypes.c_long, _c_float_p, ctypes.c_long, ctypes.c_int,
                                   ctypes.c_void_p, _c_float_p, ctypes.c_long, ctypes.c_void_p]),
     "gpsig_sigkern_levels": (ctypes.c_int, [_c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_long,
@@ -47,6 +49,12 @@ _PROTOTYPES = {
     "gpsig_tens_seq_kern_levels": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, _c_float_p, ctypes.c_long, ctypes.c_int,
                                                   _c_float_p, ctypes.c_long, ctypes.c_int, ctypes.c_int, _c_float_p,
                                                   ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, ctypes.c_void_p]),
+    "gpsig_lr_hadamard_csc": (ctypes.c_int, [_c_float_p, ctypes.c_long, ctypes.c_int, _c_float_p, ctypes.c_int, ctypes.c_void_p,
+                                             ctypes.c_void_p, ctypes.c_void_p, _c_float_p, ctypes.c_int, ctypes.c_float,
+                                             _c_float_p, ctypes.c_void_p]),
+    "gpsig_lr_seq_level": (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _c_float_p, ctypes.c_int,
+                                          ctypes.c_float, _c_float_p, _c_float_p, ctypes.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)

@@ -447,9 +447,45 @@ __global__ void scale_features_kernel(const float* __restrict__ X, long long tot
     }
 }
 
+// lags.py:7-63.  time grid l / (L - 1); query max(time - lag, 0); left knot = last grid point <= query (+ jitter, lags.py:23)
+__global__ void add_lags_kernel(const float* __restrict__ X, long long n, int L, int d, const float* __restrict__ lags,
+                                int num_lags, float* __restrict__ out) {
+    const int P1 = num_lags + 1;
+    const long long total = n * (long long)L * P1 * d;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % d);
+        const int pl = (int)((idx / d) % P1);
+        const int l = (int)((idx / ((long long)d * P1)) % L);
+        const long long seq = idx / ((long long)d * P1 * L);
+        const float* xs = X + seq * (long long)L * d;
+        if (pl == 0) { out[idx] = xs[(long long)l * d + c]; continue; }
+        const double Lm1 = (double)(L - 1);
+        double tq = (double)l / Lm1 - (double)lags[pl - 1];
+        if (tq < 0.0) tq = 0.0;
+        int left = (int)floor((tq + 1e-6) * Lm1 + 1e-9);  // settings.jitter = 1e-6
+        if (left > L - 2) left = L - 2;
+        if (left < 0) left = 0;
+        const double tl = (double)left / Lm1, tr = (double)(left + 1) / Lm1;
+        const double xl = xs[(long long)left * d + c], xr = xs[(long long)(left + 1) * d + c];
+        out[idx] = (float)(xl + (tq - tl) * (xr - xl) / (tr - tl));
+    }
+}
+
 }  // namespace gpsig
 
 using namespace gpsig;
+
+extern "C" int gpsig_add_lags(const float* X, long n, int L, int d, const float* lags, int num_lags, float* out, void* stream) {
+    if (!X || !out || !lags || n < 0 || L < 2 || d < 1 || num_lags < 1) return fail(GPSIG_E_BADARG, "add_lags: bad arguments");
+    const long long total = (long long)n * L * (num_lags + 1) * d;
+    if (total == 0) return GPSIG_OK;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)num_sms() * 16;
+    ProfScope prof(GPSIG_PROF_PREP, (cudaStream_t)stream, (double)n);
+    add_lags_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(X, n, L, d, lags, num_lags, out);
+    return check_launch();
+}
 
 extern "C" int gpsig_scale_features(const float* X, long rows, int d, const float* inv_lengthscales, int num_features,
                                     float* out, void* stream) {

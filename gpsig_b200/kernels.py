@@ -11,6 +11,8 @@ import numpy as np
 import torch
 
 from . import _lib, settings
+from . import low_rank_calculations as _lr
+from . import signature_algs as _algs
 
 _KIND = dict(linear=0, rbf=1, cosine=2, poly=3, mix=4, matern12=5, matern32=6, matern52=7)
 
@@ -63,6 +65,7 @@ class SignatureKernel:
         self.jitter = settings.jitter
         self.device = torch.device(device) if device is not None else None
         self._ws = None
+        self.lr_rng = np.random.default_rng()   # source of the low-rank mode's draws (reseed for reproducibility)
 
     # ---- validators (kernels.py:94-133) ----
     def _validate_number_of_features(self, input_dim, num_features):
@@ -117,15 +120,32 @@ class SignatureKernel:
         return X.index_select(-1, idx)
 
     def _seqs(self, X, presliced=False):
+        """(N, L*d) -> (N, L, d_eff): reshape (kernels.py:417-419) and, with lags, the lagged copies as extra features
+        (kernels.py:352-353 -> lags.py:41-63); scaling by lengthscales / gamma happens inside the device pipeline."""
         X = self._to_dev(X)
         if not presliced:
             X = self._slice(X)
-        return X.reshape(X.shape[0], -1, self.num_features).contiguous()                        # kernels.py:417-419
+        X = X.reshape(X.shape[0], -1, self.num_features).contiguous()
+        if self.num_lags > 0:
+            lib = _lib.load()
+            n, L, d = X.shape
+            lags = torch.as_tensor(np.asarray(self.lags, dtype=np.float32)).to(X.device)
+            out = torch.empty((n, L, (self.num_lags + 1) * d), device=X.device, dtype=torch.float32)
+            if n > 0:
+                with torch.cuda.device(X.device):
+                    rc = lib.gpsig_add_lags(X.data_ptr(), n, L, d, lags.data_ptr(), self.num_lags, out.data_ptr(), _stream())
+                _lib.check(rc, "gpsig_add_lags")
+            X = out
+        return X
 
     def _inv_ls(self, dev):
-        if self.lengthscales is None:
+        """per-feature multiplier of the (lagged) state space: gamma[p] / lengthscales[c]  (kernels.py:357-361)."""
+        if self.lengthscales is None and self.num_lags == 0:
             return None
-        return torch.as_tensor((1.0 / np.asarray(self.lengthscales, dtype=np.float64)).astype(np.float32)).to(dev)
+        inv = np.ones(self.num_features) if self.lengthscales is None else 1.0 / np.asarray(self.lengthscales, dtype=np.float64)
+        if self.num_lags > 0:
+            inv = (np.asarray(self.gamma, dtype=np.float64)[:, None] * inv[None, :]).reshape(-1)
+        return torch.as_tensor(inv.astype(np.float32)).to(dev)
 
     def _weights(self, dev):
         w = float(self.sigma) * np.asarray(self.variances, dtype=np.float64)                    # kernels.py:471
@@ -145,10 +165,6 @@ class SignatureKernel:
     def _check_supported(self):
         if self._kind is None:
             raise NotImplementedError("use a SignatureKernel subclass (SignatureLinear, SignatureRBF, ...)")
-        if self.num_lags > 0:
-            raise NotImplementedError("lags (gpsig/lags.py) are not on the B200 path yet")
-        if self.low_rank:
-            raise NotImplementedError("low-rank mode is not on the B200 path yet")
 
     def _workspace(self, dev, n1, L1, n2, L2, d):
         lib = _lib.load()
@@ -234,7 +250,7 @@ class SignatureKernel:
         out = torch.empty_like(Z)
         d = Z.shape[-1]
         with torch.cuda.device(Z.device):
-            rc = lib.gpsig_scale_features(Z.data_ptr(), Z.numel() // d, d, inv_ls.data_ptr(), self.num_features, out.data_ptr(),
+            rc = lib.gpsig_scale_features(Z.data_ptr(), Z.numel() // d, d, inv_ls.data_ptr(), inv_ls.numel(), out.data_ptr(),
                                           _stream())
         _lib.check(rc, "gpsig_scale_features")
         return out
@@ -283,6 +299,44 @@ class SignatureKernel:
         _lib.check(rc, "gpsig_tens_seq_kern_levels")
         return out
 
+    # ---- low-rank mode (kernels.py:239-261, :285-311; low_rank_calculations.py) ----
+    # Deviation from the literal reference: K() hands UNSCALED sequences to _K_seq_lr_feat (kernels.py:425,
+    # :448-449) while every other method scales first; here lengthscales / lags always apply.
+    def _lr_seeds(self):
+        return self.lr_rng.integers(0, np.iinfo(np.int32).max, size=(max(self.num_levels - 1, 1), 2))
+
+    def _lr_samples(self, *point_sets):
+        """kernels.py:444-446 / :562-563: Nystrom landmarks drawn from the union of all points of the call."""
+        pts = torch.cat([p.reshape(-1, p.shape[-1]) for p in point_sets], dim=0)
+        idx, _ = _lr._draw_indices(pts.shape[0], min(self.num_components, pts.shape[0]), self.lr_rng)
+        return pts[torch.as_tensor(idx, device=pts.device)]
+
+    def _K_seq_lr_feat(self, Xsc, nys_samples=None, seeds=None):
+        """kernels.py:239-261 on SCALED sequences (n, L, d): list of low-rank factors per level."""
+        n, L, d = Xsc.shape
+        F = _lr.Nystrom_map(Xsc.reshape(n * L, d), self._base_gram, nys_samples, self.num_components, rng=self.lr_rng)
+        return _algs.signature_kern_first_order_lr_feature(F.reshape(n, L, -1), self.num_levels, self.rank_bound, self.sparsity,
+                                                           seeds, difference=self.difference)
+
+    def _K_tens_lr_feat(self, Zsc, increments=False, nys_samples=None, seeds=None):
+        """kernels.py:285-311 on SCALED tensors."""
+        T, nz, d = Zsc.shape[0], Zsc.shape[1], Zsc.shape[-1]
+        F = _lr.Nystrom_map(Zsc.reshape(-1, d), self._base_gram, nys_samples, self.num_components, rng=self.lr_rng)
+        if increments:
+            F = F.reshape(T, nz, 2, -1)
+            F = F[:, :, 1, :] - F[:, :, 0, :]
+        else:
+            F = F.reshape(T, nz, -1)
+        return _algs.tensor_kern_lr_feature(F, self.num_levels, self.rank_bound, self.sparsity, seeds)
+
+    @staticmethod
+    def _lr_gram(PhiA, PhiB):
+        return torch.stack([a @ b.transpose(0, 1) for a, b in zip(PhiA, PhiB)], dim=0).contiguous()
+
+    @staticmethod
+    def _lr_diag(Phi):
+        return torch.stack([torch.sum(p * p, dim=-1) for p in Phi], dim=0).contiguous()
+
     # ---- public API (kernels.py:400-761) ----
     def K(self, X, X2=None, presliced=False, return_levels=False, presliced_X=False, presliced_X2=False):
         """kernels.py:400-476."""
@@ -291,9 +345,20 @@ class SignatureKernel:
             presliced_X = presliced_X2 = True
         Xs = self._seqs(X, presliced_X)
         if X2 is None:
-            lv = self._K_seq(Xs)
+            if self.low_rank:                                                                    # kernels.py:424-426
+                Phi = self._K_seq_lr_feat(self._scale_tens(Xs))
+                lv = self._lr_gram(Phi, Phi)
+            else:
+                lv = self._K_seq(Xs)
             return self._finish(lv, symmetric=True, normalize=self.normalization, return_levels=return_levels)
         X2s = self._seqs(X2, presliced_X2)
+        if self.low_rank:                                                                        # kernels.py:442-451, :456-458
+            Xc, X2c = self._scale_tens(Xs), self._scale_tens(X2s)
+            seeds, nys = self._lr_seeds(), self._lr_samples(Xc, X2c)
+            Phi, Phi2 = self._K_seq_lr_feat(Xc, nys, seeds), self._K_seq_lr_feat(X2c, nys, seeds)
+            lv = self._lr_gram(Phi, Phi2)
+            d1, d2 = (self._lr_diag(Phi), self._lr_diag(Phi2)) if self.normalization else (None, None)
+            return self._finish(lv, d1, d2, normalize=self.normalization, return_levels=return_levels)
         lv = self._K_seq(Xs, X2s)
         d1 = d2 = None
         if self.normalization:
@@ -311,19 +376,33 @@ class SignatureKernel:
                 return w[:, None].expand(-1, n).contiguous()
             return torch.full((n,), float(self.sigma * np.sum(self.variances)), device=dev, dtype=torch.float32)
         Xs = self._seqs(X, presliced)
-        lv = self._K_seq_diag(Xs)
+        if self.low_rank:                                                                        # kernels.py:499-501
+            lv = self._lr_diag(self._K_seq_lr_feat(self._scale_tens(Xs)))
+        else:
+            lv = self._K_seq_diag(Xs)
         return self._finish(lv[:, :, None].contiguous(), normalize=False, return_levels=return_levels).squeeze(-1)
 
     def K_tens(self, Z, return_levels=False, increments=False):
         """kernels.py:512-536."""
         self._check_supported()
-        lv = self._K_tens(self._scale_tens(Z), increments)
+        if self.low_rank:                                                                        # kernels.py:525-527
+            Phi = self._K_tens_lr_feat(self._scale_tens(Z), increments)
+            lv = self._lr_gram(Phi, Phi)
+        else:
+            lv = self._K_tens(self._scale_tens(Z), increments)
         return self._finish(lv, normalize=False, return_levels=return_levels)
 
     def K_tens_vs_seq(self, Z, X, return_levels=False, increments=False, presliced=False):
         """kernels.py:538-588."""
         self._check_supported()
         Xs = self._seqs(X, presliced)
+        if self.low_rank:                                                                        # kernels.py:560-568, :573-574
+            Zc, Xc = self._scale_tens(Z), self._scale_tens(Xs)
+            seeds, nys = self._lr_seeds(), self._lr_samples(Zc, Xc)
+            PhiZ, PhiX = self._K_tens_lr_feat(Zc, increments, nys, seeds), self._K_seq_lr_feat(Xc, nys, seeds)
+            lv = self._lr_gram(PhiZ, PhiX)
+            d2 = self._lr_diag(PhiX) if self.normalization else None
+            return self._finish(lv, None, d2, normalize=self.normalization, return_levels=return_levels)
         lv = self._K_tens_vs_seq(Z, Xs, increments)
         d2 = self._K_seq_diag(Xs) if self.normalization else None
         return self._finish(lv, None, d2, normalize=self.normalization, return_levels=return_levels)
@@ -332,15 +411,23 @@ class SignatureKernel:
         """kernels.py:590-671."""
         self._check_supported()
         Xs = self._seqs(X, presliced)
-        Kzz = self._finish(self._K_tens(self._scale_tens(Z), increments), normalize=False, return_levels=return_levels)
-        Kzx_lv = self._K_tens_vs_seq(Z, Xs, increments)
+        PhiX = None
+        if self.low_rank:                                                                        # kernels.py:612-621
+            Zc, Xc = self._scale_tens(Z), self._scale_tens(Xs)
+            seeds, nys = self._lr_seeds(), self._lr_samples(Zc, Xc)
+            PhiZ, PhiX = self._K_tens_lr_feat(Zc, increments, nys, seeds), self._K_seq_lr_feat(Xc, nys, seeds)
+            Kzz = self._finish(self._lr_gram(PhiZ, PhiZ), normalize=False, return_levels=return_levels)
+            Kzx_lv = self._lr_gram(PhiZ, PhiX)
+        else:
+            Kzz = self._finish(self._K_tens(self._scale_tens(Z), increments), normalize=False, return_levels=return_levels)
+            Kzx_lv = self._K_tens_vs_seq(Z, Xs, increments)
         if full_X_cov:
-            Kxx_lv = self._K_seq(Xs)
+            Kxx_lv = self._lr_gram(PhiX, PhiX) if self.low_rank else self._K_seq(Xs)
             dg = Kxx_lv.diagonal(dim1=1, dim2=2).contiguous() if self.normalization else None       # kernels.py:632-638
             Kxx = self._finish(Kxx_lv, symmetric=True, normalize=self.normalization, return_levels=return_levels)
             Kzx = self._finish(Kzx_lv, None, dg, normalize=self.normalization, return_levels=return_levels)
         else:
-            dg = self._K_seq_diag(Xs)
+            dg = self._lr_diag(PhiX) if self.low_rank else self._K_seq_diag(Xs)
             Kzx = self._finish(Kzx_lv, None, dg, normalize=self.normalization, return_levels=return_levels)
             if self.normalization:                                                                   # kernels.py:655-661
                 w = self._weights(Xs.device)
@@ -360,19 +447,25 @@ class SignatureKernel:
         the reference (Q2); the evident intent is implemented here.
         """
         self._check_supported()
-        Xa = self._to_dev(X)
-        Xa = Xa.reshape(Xa.shape[0], -1, self.num_features).contiguous()
+        Xa = self._seqs(X, presliced=True)
         Xb = self._seqs(X2, presliced)
-        Kxx_lv = self._K_seq(Xa)
-        Kxx2_lv = self._K_seq(Xa, Xb)
+        Phi2 = None
+        if self.low_rank:                                                                        # kernels.py:693-702
+            Xac, Xbc = self._scale_tens(Xa), self._scale_tens(Xb)
+            seeds, nys = self._lr_seeds(), self._lr_samples(Xac, Xbc)
+            Phi, Phi2 = self._K_seq_lr_feat(Xac, nys, seeds), self._K_seq_lr_feat(Xbc, nys, seeds)
+            Kxx_lv, Kxx2_lv = self._lr_gram(Phi, Phi), self._lr_gram(Phi, Phi2)
+        else:
+            Kxx_lv = self._K_seq(Xa)
+            Kxx2_lv = self._K_seq(Xa, Xb)
         d1 = Kxx_lv.diagonal(dim1=1, dim2=2).contiguous() if self.normalization else None
         Kxx = self._finish(Kxx_lv, symmetric=True, normalize=self.normalization, return_levels=return_levels)
         if full_X2_cov:
-            K22_lv = self._K_seq(Xb)
+            K22_lv = self._lr_gram(Phi2, Phi2) if self.low_rank else self._K_seq(Xb)
             d2 = K22_lv.diagonal(dim1=1, dim2=2).contiguous() if self.normalization else None
             K22 = self._finish(K22_lv, symmetric=True, normalize=self.normalization, return_levels=return_levels)
         else:
-            d2 = self._K_seq_diag(Xb)
+            d2 = self._lr_diag(Phi2) if self.low_rank else self._K_seq_diag(Xb)
             if self.normalization:
                 w = self._weights(Xb.device)
                 K22 = w[:, None].expand(-1, Xb.shape[0]).contiguous()

@@ -5,6 +5,7 @@ tensors in and out, every call is one C-ABI entry point of libgpsig_b200.so.
 import torch
 
 from . import _lib
+from . import low_rank_calculations as _lr
 
 
 def _stream():
@@ -94,3 +95,46 @@ def signature_kern_tens_vs_seq_higher_order(M, num_levels, order=2, difference=T
     """signature_algs.py:129-160."""
     order = num_levels if (order <= 0 or order >= num_levels) else order
     return _tens_vs_seq(M, num_levels, order, difference)
+
+
+def _level_seed(seeds, i):
+    return None if seeds is None else seeds[i]
+
+
+def signature_kern_first_order_lr_feature(U, num_levels, rank_bound, sparsity='sqrt', seeds=None, difference=True,
+                                          projections=None, literal=False):
+    """signature_algs.py:162-192.  U (n, L, C) low-rank features of the embedded sequences -> list of num_levels+1
+    factors.  `seeds` ((num_levels-1, 2) ints) or `projections` (list of low_rank_calculations.Projection) fix the
+    random projections; literal=True reproduces the reference's :191 (every level >= 2 repeats level 1)."""
+    U = _f32(U)
+    n = U.shape[0]
+    Phi = [torch.ones((n, 1), device=U.device, dtype=torch.float32)]
+    if difference:
+        U = (U[:, 1:, :] - U[:, :-1, :]).contiguous()
+    first = U.sum(dim=1)
+    Phi.append(first)
+    P = U
+    for i in range(2, num_levels + 1):
+        proj = projections[i - 2] if projections is not None else _lr.draw_projection(
+            U.shape[-1], P.shape[-1], rank_bound, sparsity, seed=_level_seed(seeds, i - 2), device=U.device)
+        P, phiP = _lr.lr_seq_level(U, P, proj)
+        Phi.append(first if literal else phiP)
+    return Phi
+
+
+def tensor_kern_lr_feature(U, num_levels, rank_bound, sparsity='sqrt', seeds=None, projections=None):
+    """signature_algs.py:194-222.  U (T, nz, C) -> list of num_levels+1 factors (nz, .)."""
+    U = _f32(U)
+    nz = U.shape[1]
+    Phi = [torch.ones((nz, 1), device=U.device, dtype=torch.float32)]
+    k = 0
+    for i in range(1, num_levels + 1):
+        R = U[k].contiguous()
+        k += 1
+        for j in range(1, i):
+            proj = projections[j - 1] if projections is not None else _lr.draw_projection(
+                U.shape[-1], R.shape[-1], rank_bound, sparsity, seed=_level_seed(seeds, j - 1), device=U.device)
+            R = _lr.lr_hadamard_prod_rand(U[k].contiguous(), R, proj)
+            k += 1
+        Phi.append(R)
+    return Phi

@@ -80,6 +80,13 @@ int gpsig_scale_features(const float* X, long rows, int d, const float* inv_leng
                          float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * a2  gpsig/lags.py:7-63 (add_lags_to_sequences; called at kernels.py:352-353): out[n, l, 0, :] = X[n, l, :] and
+ *     out[n, l, 1 + p, :] = X[n] linearly interpolated at time max(l / (L-1) - lags[p], 0).
+ *     X (n, L, d), lags (num_lags) device pointers; out (n, L, (num_lags + 1) * d).
+ * ------------------------------------------------------------------------------------------------------------- */
+int gpsig_add_lags(const float* X, long n, int L, int d, const float* lags, int num_lags, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * a3  static-kernel Gram, kernels.py:225-230 (`self._base_kern(X, X2)`) on already-scaled points.
  *     X (rows1, d), X2 (rows2, d) row-major; out (rows1, rows2) with leading dimension ld (elements).
  *     X2 == NULL means X2 = X.  `params` are the kernel's extra scalars (see enum), may be NULL.
@@ -156,6 +163,22 @@ int gpsig_tens_vs_seq_levels(const float* M, int num_levels, long nz, long n, in
 int gpsig_tens_seq_kern_levels(int kind, const float* params, const float* Z, long nz, int increments, const float* X,
                                long n, int L, int d, const float* inv_lengthscales, int num_levels, int order,
                                int difference, float* out_levels, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * a15  low-rank mode.  The random projection of low_rank_calculations.py:152-193 (very sparse Gaussian JL, matrix R of
+ *     shape (k1*k2, r); row q pairs A[..., q % k1] with B[..., q / k1]) is passed in compressed-sparse-column form:
+ *     colptr (r+1), and per non-zero ia = row % k1, ib = row / k1, val = R[row, col]; scale = sqrt(s / r).
+ *     The coordinate-subsampling variant (:104-127) is one non-zero per column (val = Rademacher sign), scale = 1.
+ *     Randomness is the caller's (TensorFlow's streams are not reproducible): parity is defined on given draws.
+ *       gpsig_lr_hadamard_csc: C[x, c] = scale * sum_e A[x, ia[e]] * B[x, ib[e]] * val[e];  A (rows,k1) B (rows,k2) C (rows,r)
+ *       gpsig_lr_seq_level   : one iteration of signature_algs.py:182-188 --
+ *                              P_out[n,t,:] = proj(U[n,t,:], sum_{t'<t} P_in[n,t',:]),  phi[n,:] = sum_t P_out[n,t,:]
+ *                              U (n, Lr, k1), P_in (n, Lr, k2), P_out (n, Lr, r), phi (n, r)
+ * ------------------------------------------------------------------------------------------------------------- */
+int gpsig_lr_hadamard_csc(const float* A, long rows, int k1, const float* B, int k2, const int* colptr, const int* ia,
+                          const int* ib, const float* val, int r, float scale, float* out, void* stream);
+int gpsig_lr_seq_level(const float* U, const float* P_in, long n, int Lr, int k1, int k2, const int* colptr, const int* ia,
+                       const int* ib, const float* val, int r, float scale, float* P_out, float* phi, void* stream);
 
 #ifdef __cplusplus
 }
