@@ -7,6 +7,8 @@
 //    store-bound by design: each thread keeps its 4 points y_{j,t..t+3} in registers for the whole row block and emits
 //    one 16-byte store per (i, s); a warp writes 512 contiguous bytes.
 //  * gram_kernel: plain (rows1 x rows2) Gram for the operator-level API (compute_base_kern_symm, K_tens, ...).
+#include <string.h>
+
 #include "internal.cuh"
 
 namespace gpsig {
@@ -21,6 +23,7 @@ template <> struct KernTraits<GPSIG_KERN_MIX>      { static constexpr bool dot =
 template <> struct KernTraits<GPSIG_KERN_MATERN12> { static constexpr bool dot = false, sq = true,  norms = false; };
 template <> struct KernTraits<GPSIG_KERN_MATERN32> { static constexpr bool dot = false, sq = true,  norms = false; };
 template <> struct KernTraits<GPSIG_KERN_MATERN52> { static constexpr bool dot = false, sq = true,  norms = false; };
+template <> struct KernTraits<GPSIG_KERN_SPECTRAL> { static constexpr bool dot = false, sq = false, norms = false; };
 
 template <int KIND>
 __device__ __forceinline__ float kern_eval(float dot, float sq, float xx, float yy, const KernParams& kp) {
@@ -138,6 +141,10 @@ __global__ void __launch_bounds__(256) delta_producer_kernel(const ProdParams p)
             const float xn = (KT::norms) ? sAn[s] : 0.f;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
+                if (KIND == GPSIG_KERN_SPECTRAL) {
+                    f[u] = spectral_eval(sA + s * DP, y[u], DP, p.kp);
+                    continue;
+                }
                 float dot = 0.f, sq = 0.f;
 #pragma unroll
                 for (int c = 0; c < DP; ++c) {
@@ -157,7 +164,8 @@ __global__ void __launch_bounds__(256) delta_producer_kernel(const ProdParams p)
                         if (KT::dot) dot = fmaf(xv, y[NPT - 1][c], dot);
                         if (KT::sq) { const float df = xv - y[NPT - 1][c]; sq = fmaf(df, df, sq); }
                     }
-                    f[4] = kern_eval<KIND>(dot, sq, xn, yn[NPT - 1], p.kp);
+                    f[4] = KIND == GPSIG_KERN_SPECTRAL ? spectral_eval(sA + s * DP, y[NPT - 1], DP, p.kp)
+                                                       : kern_eval<KIND>(dot, sq, xn, yn[NPT - 1], p.kp);
                 }
                 if (s > 0 && active) {
                     float4 o;
@@ -203,16 +211,20 @@ __global__ void __launch_bounds__(256) delta_producer_fast_kernel(const ProdPara
     const int t0 = (threadIdx.x % tpp) * 4;
     const bool active = jl < p.nj;
     const int j = p.j0 + (active ? jl : p.nj - 1);
-    const bool direct5 = RBF && ((threadIdx.x % tpp == tpp - 1) || (threadIdx.x & 31) == 31) && (t0 + 4 < p.rowsB) &&
-                         (t0 + 3 < p.ncols);  // the right-hand neighbour column is not held by the next lane of this warp
-    // warp-uniform: does any lane of this warp have to evaluate its halo column itself?  (never when P == rowsB)
-    const bool any5 = RBF && __any_sync(0xffffffffu, direct5);
+    // RBF: the column to the right (t0 + 4) comes from the next lane by shuffle unless that lane is in another warp or
+    // another pair (`bnd`); then the thread evaluates it itself (direct5) or, past the last point, reuses its own column.
+    // Columns past the sequence need no masking: RBF clamps them to the last point (equal values difference to exactly
+    // zero), LINEAR gives them zero increments.
+    const bool bnd = (threadIdx.x % tpp == tpp - 1) || (threadIdx.x & 31) == 31;
+    const bool direct5 = RBF && bnd && (t0 + 4 < p.rowsB);
+    const bool any5 = RBF && __any_sync(0xffffffffu, direct5);  // warp-uniform (never true when P == rowsB)
     float2 y[NPT][H];
 #pragma unroll
     for (int u = 0; u < NPT; ++u) {
         const int t = t0 + u;
-        const bool ok = t < p.rowsB && (u < 4 || direct5);
-        const float2* src = reinterpret_cast<const float2*>(p.B + ((long long)j * p.rowsB + (ok ? t : 0)) * DPA);
+        const bool ok = RBF || t < p.rowsB;
+        const int tc = t < p.rowsB ? t : p.rowsB - 1;
+        const float2* src = reinterpret_cast<const float2*>(p.B + ((long long)j * p.rowsB + tc) * DPA);
 #pragma unroll
         for (int h = 0; h < H; ++h) y[u][h] = ok ? src[h] : make_float2(0.f, 0.f);
         if (RBF) {  // y side of the augmented product: (..., 1, -|y|^2/2)
@@ -245,21 +257,16 @@ __global__ void __launch_bounds__(256) delta_producer_fast_kernel(const ProdPara
             orow = p.out + (w * p.SR + n * p.out_rows + (t0 >> 4)) * kSkewRowFloats + (sw >> 2);
             row_stride = kSkewRowFloats;
         }
-        float fprev[NPT];
-#pragma unroll
-        for (int u = 0; u < NPT; ++u) fprev[u] = 0.f;
-        for (int s = 0; s < p.rowsA; ++s) {
+        // f[0..3] (and the halo f[4] for RBF) of row s
+        auto eval_row = [&](int s, float (&f)[NPT]) {
             float2 x[H];
-            {
-                const float4* xs = reinterpret_cast<const float4*>(sA + s * DPA);
+            const float4* xs = reinterpret_cast<const float4*>(sA + s * DPA);
 #pragma unroll
-                for (int h4 = 0; h4 < DPA / 4; ++h4) {
-                    const float4 v = xs[h4];
-                    x[2 * h4] = make_float2(v.x, v.y);
-                    x[2 * h4 + 1] = make_float2(v.z, v.w);
-                }
+            for (int h4 = 0; h4 < DPA / 4; ++h4) {
+                const float4 v = xs[h4];
+                x[2 * h4] = make_float2(v.x, v.y);
+                x[2 * h4 + 1] = make_float2(v.z, v.w);
             }
-            float f[NPT];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 float2 acc = make_float2(0.f, 0.f);
@@ -269,7 +276,8 @@ __global__ void __launch_bounds__(256) delta_producer_fast_kernel(const ProdPara
                 f[u] = RBF ? ex2_approx(v) : v;
             }
             if (RBF) {
-                f[NPT - 1] = __shfl_down_sync(0xffffffffu, f[0], 1);
+                const float nb = __shfl_down_sync(0xffffffffu, f[0], 1);
+                f[NPT - 1] = bnd ? f[3] : nb;
                 if (any5) {  // uniform branch
                     float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
@@ -277,23 +285,29 @@ __global__ void __launch_bounds__(256) delta_producer_fast_kernel(const ProdPara
                     const float v = ex2_approx(acc.x + acc.y);
                     if (direct5) f[NPT - 1] = v;
                 }
-                if (s > 0 && active) {
-                    float4 o;
-                    o.x = (t0 + 0 < p.ncols) ? (f[1] - f[0]) - (fprev[1] - fprev[0]) : 0.f;
-                    o.y = (t0 + 1 < p.ncols) ? (f[2] - f[1]) - (fprev[2] - fprev[1]) : 0.f;
-                    o.z = (t0 + 2 < p.ncols) ? (f[3] - f[2]) - (fprev[3] - fprev[2]) : 0.f;
-                    o.w = (t0 + 3 < p.ncols) ? (f[NPT - 1] - f[3]) - (fprev[NPT - 1] - fprev[3]) : 0.f;
-                    *reinterpret_cast<float4*>(orow + (long long)(s - 1) * row_stride) = o;
-                }
+            }
+        };
+        if (RBF) {
+            float fprev[NPT], f[NPT];
+            eval_row(0, fprev);
+            float* o = orow;
+            for (int s = 1; s < p.rowsA; ++s, o += row_stride) {
+                eval_row(s, f);
+                float4 v;
+                v.x = (f[1] - f[0]) - (fprev[1] - fprev[0]);
+                v.y = (f[2] - f[1]) - (fprev[2] - fprev[1]);
+                v.z = (f[3] - f[2]) - (fprev[3] - fprev[2]);
+                v.w = (f[NPT - 1] - f[3]) - (fprev[NPT - 1] - fprev[3]);
+                if (active) *reinterpret_cast<float4*>(o) = v;
 #pragma unroll
                 for (int u = 0; u < NPT; ++u) fprev[u] = f[u];
-            } else if (active) {
-                float4 o;
-                o.x = (t0 + 0 < p.ncols) ? f[0] : 0.f;
-                o.y = (t0 + 1 < p.ncols) ? f[1] : 0.f;
-                o.z = (t0 + 2 < p.ncols) ? f[2] : 0.f;
-                o.w = (t0 + 3 < p.ncols) ? f[3] : 0.f;
-                *reinterpret_cast<float4*>(orow + (long long)s * row_stride) = o;
+            }
+        } else {
+            float f[NPT];
+            float* o = orow;
+            for (int s = 0; s < p.rowsA; ++s, o += row_stride) {
+                eval_row(s, f);
+                if (active) *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
             }
         }
     }
@@ -387,6 +401,7 @@ int launch_delta_producer(int kind, const ProdParams& p, int DP, bool diff2d, cu
         case GPSIG_KERN_MATERN12: return launch_producer_kind<GPSIG_KERN_MATERN12>(p, DP, diff2d, st);
         case GPSIG_KERN_MATERN32: return launch_producer_kind<GPSIG_KERN_MATERN32>(p, DP, diff2d, st);
         case GPSIG_KERN_MATERN52: return launch_producer_kind<GPSIG_KERN_MATERN52>(p, DP, diff2d, st);
+        case GPSIG_KERN_SPECTRAL: return launch_producer_kind<GPSIG_KERN_SPECTRAL>(p, DP, diff2d, st);
     }
     return fail(GPSIG_E_BADARG, "unknown static kernel kind %d", kind);
 }
@@ -420,7 +435,7 @@ __global__ void gram_kernel(const float* __restrict__ X, long long rows1, const 
         xx = fmaf(a, a, xx);
         yy = fmaf(b, b, yy);
     }
-    out[r * ld + c] = kern_eval<KIND>(dot, sq, xx, yy, kp);
+    out[r * ld + c] = KIND == GPSIG_KERN_SPECTRAL ? spectral_eval(x, y, d, kp) : kern_eval<KIND>(dot, sq, xx, yy, kp);
 }
 
 template <int KIND>
@@ -432,7 +447,24 @@ static int launch_gram_kind(const float* X, long long r1, const float* X2, long 
 }
 
 KernParams make_kern_params(int kind, const float* params) {
-    KernParams kp{0.f, 0.f};
+    KernParams kp;
+    memset(&kp, 0, sizeof(kp));
+    if (kind == GPSIG_KERN_SPECTRAL && params) {  // {family, Q, d, alpha[Q], omega[Q*d], gamma[Q*d]}; sizes clamped
+        kp.fam = (int)params[0];
+        int Q = (int)params[1], d = (int)params[2];
+        const int Qc = Q < kSpecMaxQ ? Q : kSpecMaxQ, dc = d < kSpecMaxD ? d : kSpecMaxD;
+        kp.Q = Qc;
+        const float* al = params + 3;
+        const float* om = al + Q;
+        const float* ga = om + (size_t)Q * d;
+        for (int q = 0; q < Qc; ++q) {
+            kp.alpha[q] = al[q];
+            for (int c = 0; c < dc; ++c) {
+                kp.omega[q * kSpecMaxD + c] = om[q * d + c];
+                kp.gamma[q * kSpecMaxD + c] = ga[q * d + c];
+            }
+        }
+    }
     if (kind == GPSIG_KERN_POLY) { kp.a = params ? params[0] : 1.f; kp.b = params ? params[1] : 3.f; }
     if (kind == GPSIG_KERN_MIX) kp.a = params ? params[0] : 0.5f;
     return kp;
@@ -515,6 +547,9 @@ extern "C" int gpsig_gram(int kind, const float* X, long rows1, const float* X2,
         case GPSIG_KERN_MATERN12: return launch_gram_kind<GPSIG_KERN_MATERN12>(X, rows1, X2, rows2, d, kp, out, ld, st);
         case GPSIG_KERN_MATERN32: return launch_gram_kind<GPSIG_KERN_MATERN32>(X, rows1, X2, rows2, d, kp, out, ld, st);
         case GPSIG_KERN_MATERN52: return launch_gram_kind<GPSIG_KERN_MATERN52>(X, rows1, X2, rows2, d, kp, out, ld, st);
+        case GPSIG_KERN_SPECTRAL:
+            if (d > kSpecMaxD) return fail(GPSIG_E_UNSUPPORTED, "spectral kernel supports at most %d features", kSpecMaxD);
+            return launch_gram_kind<GPSIG_KERN_SPECTRAL>(X, rows1, X2, rows2, d, kp, out, ld, st);
     }
     return fail(GPSIG_E_BADARG, "unknown static kernel kind %d", kind);
 }

@@ -4,9 +4,38 @@
 
 namespace gpsig {
 
+constexpr int kSpecMaxQ = 8, kSpecMaxD = 16;
 struct KernParams {
     float a, b;  // poly: gamma, degree; mix: mixing
+    // spectral (kernels.py:894-942): Q mixture components, per-feature frequencies omega and inverse scales gamma
+    int Q, fam;  // fam 0: exp(-|g d|^2 / 2), 1: exp(-|g d| / 2)
+    float alpha[kSpecMaxQ];
+    float omega[kSpecMaxQ * kSpecMaxD];
+    float gamma[kSpecMaxQ * kSpecMaxD];
 };
+
+#if defined(__CUDACC__)
+// sum_q alpha_q * env(|gamma_q * (x - y)|) * cos(2 pi <omega_q, x - y>)   (kernels.py:921-942)
+template <typename XA, typename YA>
+__device__ __forceinline__ float spectral_eval(const XA& x, const YA& y, int n, const KernParams& kp) {
+    float acc = 0.f;
+    for (int q = 0; q < kp.Q; ++q) {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < kSpecMaxD; ++c) {
+            if (c < n) {
+                const float df = x[c] - y[c];
+                const float g = df * kp.gamma[q * kSpecMaxD + c];
+                s1 = fmaf(g, g, s1);
+                s2 = fmaf(df, kp.omega[q * kSpecMaxD + c], s2);
+            }
+        }
+        const float env = kp.fam == 1 ? __expf(-0.5f * sqrtf(s1)) : __expf(-0.5f * s1);
+        acc = fmaf(kp.alpha[q] * env, cospif(2.f * s2), acc);
+    }
+    return acc;
+}
+#endif
 
 // ---- work-item enumeration shared by the chunk producer and the recursion kernels ---------------------------------
 // An item is a group of G neighbouring pairs (i, jg*G .. jg*G+G-1).  Items are numbered row by row.

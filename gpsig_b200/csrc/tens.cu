@@ -176,7 +176,8 @@ __global__ void __launch_bounds__(128) tens_seq_fused_kernel(const TsfParams p) 
                     const float df = a - b;
                     sq = fmaf(df, df, sq);
                 }
-                const float f = kern_eval_t<KIND>(dot, sq, szn[k * ninc + w], xn, p.kp);
+                const float f = KIND == GPSIG_KERN_SPECTRAL ? spectral_eval(zp, x, DP, p.kp)
+                                                            : kern_eval_t<KIND>(dot, sq, szn[k * ninc + w], xn, p.kp);
                 v = (ninc == 2) ? (w == 0 ? -f : v + f) : f;
             }
             h[k] = p.difference ? v - hprev[k] : v;
@@ -505,6 +506,7 @@ extern "C" int gpsig_tens_seq_kern_levels(int kind, const float* params, const f
             case GPSIG_KERN_MATERN12: rc = launch_tsf<GPSIG_KERN_MATERN12>(p, st); break;
             case GPSIG_KERN_MATERN32: rc = launch_tsf<GPSIG_KERN_MATERN32>(p, st); break;
             case GPSIG_KERN_MATERN52: rc = launch_tsf<GPSIG_KERN_MATERN52>(p, st); break;
+            case GPSIG_KERN_SPECTRAL: rc = launch_tsf<GPSIG_KERN_SPECTRAL>(p, st); break;
             default: rc = fail(GPSIG_E_BADARG, "unknown static kernel kind %d", kind);
         }
     }

@@ -14,7 +14,7 @@ from . import _lib, settings
 from . import low_rank_calculations as _lr
 from . import signature_algs as _algs
 
-_KIND = dict(linear=0, rbf=1, cosine=2, poly=3, mix=4, matern12=5, matern32=6, matern52=7)
+_KIND = dict(linear=0, rbf=1, cosine=2, poly=3, mix=4, matern12=5, matern32=6, matern52=7, spectral=8)
 
 
 def _stream():
@@ -565,6 +565,39 @@ class SignatureMix(SignatureKernel):
 
     def _static_params(self):
         return [self.mixing]
+
+
+class SignatureSpectral(SignatureKernel):
+    """kernels.py:894-942.  Families 'gauss' / 'exp'; 'mixed' references an undefined name upstream."""
+    _kind = "spectral"
+
+    def __init__(self, input_dim, num_features, num_levels, family='gauss', Q=5, **kwargs):
+        kwargs.pop("lengthscales", None)
+        super().__init__(input_dim, num_features, num_levels, lengthscales=None, **kwargs)
+        if family in ('exp', 'exponential'):
+            self.family = 'exp'
+        elif family in ('gauss', 'gaussian', 'rbf'):
+            self.family = 'rbf'
+        elif family in ('mixed', 'mix'):
+            raise NotImplementedError("the 'mixed' spectral family is broken in the reference (kernels.py:932 uses an undefined Q)")
+        else:
+            raise ValueError("Unrecognized spectral family name.")
+        if Q > 8 or self.num_features * (self.num_lags + 1) > 16:
+            raise NotImplementedError("the device spectral kernel supports Q <= 8 and at most 16 (lagged) features")
+        self.Q = int(Q)
+        lag_gamma = getattr(self, "gamma", None)          # the lag weights of the base class share the reference's attribute name
+        self.alpha = np.exp(np.random.randn(Q))                                                   # kernels.py:913-915
+        self.omega = np.exp(np.random.randn(Q, self.num_features))
+        self.spec_gamma = np.exp(np.random.randn(Q, self.num_features))
+        if lag_gamma is not None:
+            self.gamma = lag_gamma
+
+    def _static_params(self):
+        reps = self.num_lags + 1
+        om = np.tile(np.asarray(self.omega, dtype=np.float64), (1, reps))
+        ga = np.tile(np.asarray(self.spec_gamma, dtype=np.float64), (1, reps))
+        return [1.0 if self.family == 'exp' else 0.0, float(self.Q), float(om.shape[1])] + list(np.asarray(self.alpha).ravel()) \
+            + list(om.ravel()) + list(ga.ravel())
 
 
 class SignatureMatern12(SignatureKernel):

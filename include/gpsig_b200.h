@@ -41,7 +41,9 @@ enum {
     GPSIG_KERN_MIX = 4,      /* SignatureMix      kernels.py:881-892   params = {mixing} */
     GPSIG_KERN_MATERN12 = 5, /* kernels.py:955-958 */
     GPSIG_KERN_MATERN32 = 6, /* kernels.py:974-977 */
-    GPSIG_KERN_MATERN52 = 7  /* kernels.py:991-993 */
+    GPSIG_KERN_MATERN52 = 7, /* kernels.py:991-993 */
+    GPSIG_KERN_SPECTRAL = 8  /* SignatureSpectral kernels.py:894-942, families 'gauss' / 'exp' ('mixed' is broken upstream);
+                                params = {family (0 gauss, 1 exp), Q, d, alpha[Q], omega[Q*d], gamma[Q*d]}, Q <= 8, d <= 16 */
 };
 
 int gpsig_version(void);
