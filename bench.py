@@ -8,7 +8,7 @@ bench.py -- sequence-pairs/sec of the full signature-kernel covariance K(X, X) (
     python bench.py --impl reference ...      # the reference's own algorithm (fp64 NumPy oracle) on the host cores
 
 A "step" is one evaluation of K(X, X) for the whole workload: point prep -> chunked increment-Gram producer ->
-TMA-staged level recursion -> normalise / weight / sum -> mirror (gpsig_b200.kernels.SignatureKernel.K; with N > 1
+bulk-copy-staged level recursion -> normalise / weight / sum -> mirror (gpsig_b200.kernels.SignatureKernel.K; with N > 1
 gpsig_b200.parallel.sharded_K_symm: row blocks dealt over the ranks, ONE all-gather of the assembled rows).  The
 problem size is fixed as N grows ("scaling": "strong").
 
@@ -16,7 +16,7 @@ problem size is fixed as N grows ("scaling": "strong").
             steps).
   e2e       the same through the public API with HOST buffers: X starts in pinned host memory, K ends in pinned
             host memory, both copies inside the timed region.
-  roofline  the dominant kernel (sigkern_fo_tma_kernel, the level recursion): algorithmic bytes per pair
+  roofline  the dominant kernel (sigkern_fo_stream_kernel, the level recursion): algorithmic bytes per pair
             (4 L1 L2 + 4 (M+1)) x pairs processed / its own CUDA-event duration (events recorded around
             every launch inside the library: gpsig_profile_*), against MEASURED_PEAKS.json's hbm_gbs.
   cpu_baseline  the fp64 NumPy oracle (op-for-op restatement of the reference, oracle/gpsig_oracle.py) on a bounded
@@ -315,7 +315,7 @@ def run_ours(args, wl):
     r_ms, r_n, r_units = prof["recursion"]
     achieved = (r_units * b_pair) / (r_ms * 1e-3) / 1e9 if r_ms > 0 else 0.0
     traffic = load_traffic("%s_recursion_bytes_per_launch" % args.workload) if world == 1 else None
-    roofline = {"bound": "hbm", "kernel": "sigkern_fo_tma_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "sigkern_fo_stream_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "bytes_per_pair": b_pair, "pairs_per_launch": r_units / max(r_n, 1), "launches": r_n,
                 "avg_launch_ms": r_ms / max(r_n, 1), "kernel_share_of_step": r_ms / ms_total}
