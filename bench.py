@@ -22,7 +22,8 @@ problem size is fixed as N grows ("scaling": "strong").
   cpu_baseline  the fp64 NumPy oracle (op-for-op restatement of the reference, oracle/gpsig_oracle.py) on a bounded
             sample (n_s x n_s pairs of the same L/d/M) over all host cores; a reported baseline, not the target.
 
-Nothing here reads /root/reference.  The only place oracle/ is executed is cpu_baseline / --impl reference.
+Nothing here reads /root/reference.  oracle/ is executed only as the CPU baseline (cpu_baseline / --impl reference) and,
+after the timed region, as the checker of a 12 x 12 corner of the result ("parity").
 """
 import argparse
 import json
@@ -324,6 +325,14 @@ def run_ours(args, wl):
     if p_ms > 0:
         stages["producer"]["store_GBps"] = p_units * 4 * (L - 1) * kernels_pitch(L) / (p_ms * 1e-3) / 1e9
 
+    # parity spot check (not timed): a corner of the matrix the timed steps produced against the fp64 oracle
+    from oracle import gpsig_oracle as O
+    nc = 12
+    ko = O.SignatureKernelOracle(kind, L * d, d, M, lengthscales=lengthscales_for(kind, d))
+    ref = ko.K(Xnp[:nc].astype(np.float64))
+    parity = {"corner": "%dx%d" % (nc, nc), "max_abs_err_over_max_abs_ref": float(np.max(np.abs(Kh.numpy()[:nc, :nc] - ref)) / np.max(np.abs(ref))),
+              "tolerance": 1e-4}
+
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         cpu_baseline, _ = time_cpu_reference(kind, L, d, M, args.cpu_sample_n, 1, 0)
@@ -342,6 +351,7 @@ def run_ours(args, wl):
         "clocks": clocks,
         "roofline": roofline,
         "stages": stages,
+        "parity": parity,
         "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line), flush=True)

@@ -230,7 +230,7 @@ struct TsfFastParams {
     float* out;       // (NLEV + 1, nz, n)
 };
 
-constexpr int kTsfZPerBlock = 8;   // warps per block, one inducing tensor each
+constexpr int kTsfZPerBlock = 4;   // warps per block, one inducing tensor each (3 blocks / SM at ~160 registers)
 constexpr int kTsfSeqPerThread = 2;
 
 template <bool RBF, int NLEV, int DPA>
@@ -268,22 +268,32 @@ __global__ void __launch_bounds__(kTsfZPerBlock * 32) tens_seq_fast_kernel(const
 #pragma unroll
         for (int k = 0; k < T; ++k) { c[a][k] = 0.f; vprev[a][k] = 0.f; }
     const bool tdiff = RBF && p.difference;  // LINEAR takes its time difference from the prepared increments
-    for (int t = 0; t < p.rowsX; ++t) {
-        float2 x[NS][H];
+    // the point of time step t + 1 is fetched while step t is computed
+    float2 xnext[NS][H];
+    auto fetch = [&](int t, float2 (&dst)[NS][H]) {
 #pragma unroll
         for (int a = 0; a < NS; ++a) {
             const float4* xs = reinterpret_cast<const float4*>(p.X + ((nok[a] ? nn[a] : 0) * p.rowsX + t) * DPA);
 #pragma unroll
             for (int h4 = 0; h4 < DPA / 4; ++h4) {
                 const float4 v = __ldg(xs + h4);
-                x[a][2 * h4] = make_float2(v.x, v.y);
-                x[a][2 * h4 + 1] = make_float2(v.z, v.w);
+                dst[a][2 * h4] = make_float2(v.x, v.y);
+                dst[a][2 * h4 + 1] = make_float2(v.z, v.w);
             }
             if (RBF) {  // sequence side of the augmented product: (..., 1, -|x|^2/2)
-                const float2 q = x[a][H - 2];
-                x[a][H - 2] = make_float2(q.y, q.x);
+                const float2 q = dst[a][H - 2];
+                dst[a][H - 2] = make_float2(q.y, q.x);
             }
         }
+    };
+    fetch(0, xnext);
+    for (int t = 0; t < p.rowsX; ++t) {
+        float2 x[NS][H];
+#pragma unroll
+        for (int a = 0; a < NS; ++a)
+#pragma unroll
+            for (int h = 0; h < H; ++h) x[a][h] = xnext[a][h];
+        if (t + 1 < p.rowsX) fetch(t + 1, xnext);
         int k = 0;
 #pragma unroll
         for (int m = 1; m <= NLEV; ++m) {
