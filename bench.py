@@ -289,7 +289,7 @@ def run_ours(args, wl):
     lib.gpsig_profile_enable(0)
     import ctypes
     prof = {}
-    for name, c in (("prep", 0), ("producer", 1), ("recursion", 2), ("recursion_other", 3), ("epilogue", 4)):
+    for name, c in (("prep", 0), ("producer", 1), ("recursion", 2), ("recursion_other", 3), ("epilogue", 4), ("fused", 6)):
         ms, n, un = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
         _lib.check(lib.gpsig_profile_read(c, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(un)), "gpsig_profile_read")
         prof[name] = (ms.value, n.value, un.value)

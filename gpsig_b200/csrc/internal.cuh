@@ -118,6 +118,11 @@ int launch_sigkern_fo(const float* M, int n1, int Lrows, int n2, int ncols, int 
 int launch_sigkern_stream(const float* buf, const StreamGeom& g, long long nitems, int n1, int n2, int rows, int LP, int nlev,
                           int upper_only, int i_off, int j_off, long long ldo, long long lvl_stride, float* out,
                           cudaStream_t st);
+// Fused Gram + recursion (fused.cu): level stacks straight from prepared points, no chunk buffer.
+bool fused_supported(bool rbf, int d, int nlev, int LP, int rowsA);
+int launch_sigkern_fused(bool rbf, const float* A, const float* B, int rowsA, int rowsB, int d, int DPA, int P, int LP,
+                         long long nitems, int n1, int n2, int nlev, int upper_only, int i_off, int j_off, long long ldo,
+                         long long lvl_stride, float* out, cudaStream_t st);
 // Higher-order recursion (signature_algs.py:37-74), same addressing.
 int launch_sigkern_ho(const float* M, int n1, int Lrows, int n2, int ncols, long long si, long long ss, long long sj,
                       int nlev, int order, int difference, int upper_only, int i_off, int j_off, long long ldo,

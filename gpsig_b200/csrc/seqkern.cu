@@ -192,6 +192,23 @@ extern "C" int gpsig_seq_kern_levels(int kind, const float* params, const float*
     const bool use_ho = order > 1;
     const bool upper = symmetric;
     const bool use_stream = pl.fast && !use_ho && num_levels <= 8;
+    // fused path: the increment Gram never leaves the SM (no chunk buffer, one launch for the whole row range)
+    if (use_stream && pl.fast_prod && fused_supported(kind == GPSIG_KERN_RBF, d, num_levels, pl.LP, pl.rowsA)) {
+        const int j_off = upper ? (row_begin / pl.G) * pl.G : 0;
+        const int nj = n2 - j_off, njg = (nj + pl.G - 1) / pl.G, ib = row_end - row_begin;
+        const long long nitems = items_before(ib, njg, pl.G, upper ? 1 : 0, row_begin, j_off);
+        rc = launch_sigkern_fused(kind == GPSIG_KERN_RBF, A, B, pl.rowsA, pl.rowsB, d, pl.DP, pl.P, pl.LP, nitems, ib, nj,
+                                  num_levels, upper ? 1 : 0, row_begin, j_off, n2, per_level, out_base, st);
+        if (rc != GPSIG_E_UNSUPPORTED) {
+            if (rc) return rc;
+            if (mirror && n1 > 1) {
+                ProfScope prof(GPSIG_PROF_EPILOGUE, st, (double)per_level * nl);
+                mirror_upper_kernel<<<grid_for(per_level * nl, 256), 256, 0, st>>>(out_levels, n1, nl);
+                rc = check_launch();
+            }
+            return rc;
+        }
+    }
     int i0 = row_begin;
     while (i0 < row_end) {
         const int j_off = upper ? (i0 / pl.G) * pl.G : 0;

@@ -18,46 +18,17 @@
 //     before it is needed, so neither LDS nor mbarrier latency sits on the critical path.
 #include <stdlib.h>
 
-#include <type_traits>
-
-#include "internal.cuh"
+#include "stream_consumer.cuh"
 
 namespace gpsig {
 
-constexpr int kSW = 16;               // columns per lane strip
-constexpr int kRowBytes = 2048;       // one skewed row: G pairs x (16 LP) columns x 4 B, G * LP == 32
 constexpr int kStreamMaxLevels = 8;
 
 struct StParams {
     const float* buf;
-    long long nitems;
     long long SR;     // skewed rows per stream
-    int NW;           // streams in the launch (grid * ncw)
-    int R, S;         // rows per stage, stages per ring
-    int Lin;          // increment rows per item
-    int LP, log2LP, G;
-    int njg;          // pair groups per row of the pair block
-    int n1, n2;
-    int upper_only, i_off, j_off;
-    long long ldo;
-    float* out;
-    long long out_level_stride;
+    StreamItems it;
 };
-
-__device__ __forceinline__ void st_decode_item(const StParams& p, long long u, int& i, int& jg) {
-    if (!p.upper_only) {
-        i = (int)(u / p.njg);
-        jg = (int)(u - (long long)i * p.njg);
-        return;
-    }
-    int lo = 0, hi = p.n1 - 1;
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (items_before(mid, p.njg, p.G, 1, p.i_off, p.j_off) <= u) lo = mid; else hi = mid - 1;
-    }
-    i = lo;
-    jg = (int)(u - items_before(lo, p.njg, p.G, 1, p.i_off, p.j_off)) + first_group(lo, p.G, 1, p.i_off, p.j_off);
-}
 
 // 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -65,19 +36,15 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 
 // MAXW = warps the register budget is sized for (registers are allocated in groups of 4 warps: 12 warps -> 168
 // registers per thread, enough up to 5 levels; 8 warps -> 255 for 6..8 levels).  The launch may use fewer warps.
 template <int NLEV, int MAXW>
 __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_fo_stream_kernel(const StParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    constexpr int NA = NLEV > 1 ? NLEV - 1 : 1;
     const int ncw = (blockDim.x >> 5) - 1;  // consumer warps; warp 0 is the bulk-copy producer
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int S = p.S, R = p.R, Lin = p.Lin, LP = p.LP;
+    const int S = p.it.S, R = p.it.R;
     const uint32_t stage_bytes = (uint32_t)R * kRowBytes;
     const uint32_t smem0 = smem_u32(smem);
     const uint32_t full0 = smem0 + (uint32_t)ncw * S * stage_bytes;  // full[w][s]: bytes of the stage have landed
@@ -92,16 +59,16 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_fo_stream_kernel(const S
     __syncthreads();  // the only CTA-wide barrier
 
     const int my = warp == 0 ? lane : warp - 1;  // ring / stream this thread works for
+    if (warp == 0 && lane >= ncw) return;
     const long long wg = (long long)blockIdx.x * ncw + my;
-    const long long nloc = (warp == 0 && lane >= ncw) || wg >= p.nitems ? 0 : (p.nitems - wg + p.NW - 1) / p.NW;
-    const long long total = nloc * Lin;           // increment rows of the stream
-    const long long nsteps = total + LP - 1;      // skewed rows of the stream
-    if (total == 0) return;
     const uint32_t ring = smem0 + (uint32_t)my * S * stage_bytes;
     const uint32_t fb = full0 + (uint32_t)my * S * 8, eb = empty0 + (uint32_t)my * S * 8;
 
     if (warp == 0) {
         // ===== producer: lane w streams the bytes of consumer w =====================================================
+        const long long nloc = wg >= p.it.nitems ? 0 : (p.it.nitems - wg + p.it.NW - 1) / p.it.NW;
+        const long long nsteps = nloc * p.it.Lin + p.it.LP - 1;  // skewed rows of the stream
+        if (nloc == 0) return;
         const uint8_t* src = reinterpret_cast<const uint8_t*>(p.buf) + (size_t)wg * (size_t)p.SR * kRowBytes;
         const long long nstages = (nsteps + R - 1) / R;
         int stage = 0, round = 0;
@@ -116,119 +83,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_fo_stream_kernel(const S
         }
         return;
     }
-
-    // ===== consumers ================================================================================================
-    const int l = lane & (LP - 1), q = lane >> p.log2LP;
-    // swizzled byte offsets of this lane's four 16-byte chunks inside a skewed row (same function as the writer)
-    uint32_t off[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) off[k] = swizzle_in_row((uint32_t)(q * LP * kSW * 4 + l * 64 + k * 16));
-
-    float A[NA][kSW];
-    float psum[NLEV], ksum[NLEV];
-    float g[kSW];  // increments of the current row, loaded one step ahead
-#pragma unroll
-    for (int m = 0; m < NLEV; ++m) { psum[m] = 0.f; ksum[m] = 0.f; }
-#pragma unroll
-    for (int m = 0; m < NA; ++m)
-#pragma unroll
-        for (int j = 0; j < kSW; ++j) A[m][j] = 0.f;
-
-    int lstage = 0, lrow = 0;  // stage / row-in-stage of the next skewed row to load (warp-uniform)
-    uint32_t lphase = 0;
-    uint32_t okn = 0;          // the stage about to be entered was already seen complete
-    int rho = 0;               // increment row of the current item this lane is at
-    long long item = wg;
-
-    // skewed row -> registers; on entering a stage wait for its bytes, on leaving it hand it back to the producer
-    auto load_row = [&](float (&gn)[kSW]) {
-        if (lrow == 0 && !okn) mbar_wait(fb + 8 * lstage, lphase);
-        const uint32_t base = ring + lstage * stage_bytes + lrow * kRowBytes;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(gn[4 * k]), "=f"(gn[4 * k + 1]), "=f"(gn[4 * k + 2]), "=f"(gn[4 * k + 3])
-                         : "r"(base + off[k]));
-        }
-        okn = 0;
-        if (++lrow == R) {
-            lrow = 0;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(eb + 8 * lstage);
-            if (++lstage == S) { lstage = 0; lphase ^= 1u; }
-            okn = mbar_test_wait(fb + 8 * lstage, lphase);  // looked at one step later
-        }
-    };
-
-    auto step = [&](auto check_tag, long long T) {
-        constexpr bool CHECK = decltype(check_tag)::value;
-        // running row prefixes arrive from the strip to the left (it finished this row one step ago)
-        float pin[NLEV];
-#pragma unroll
-        for (int m = 0; m < NLEV; ++m) {
-            pin[m] = __shfl_up_sync(0xffffffffu, psum[m], 1);
-            if (l == 0) pin[m] = 0.f;
-        }
-        const bool valid = CHECK ? (T - l >= 0 && T - l < total) : true;
-        float gn[kSW];
-        if (!CHECK || T + 1 < nsteps) load_row(gn);
-        float d[kSW];
-#pragma unroll
-        for (int j = 0; j < kSW; ++j) d[j] = valid ? g[j] : 0.f;
-        if (valid && rho == 0) {  // first row of an item
-#pragma unroll
-            for (int m = 0; m < NLEV; ++m) ksum[m] = 0.f;
-#pragma unroll
-            for (int m = 0; m < NA; ++m)
-#pragma unroll
-                for (int j = 0; j < kSW; ++j) A[m][j] = 0.f;
-        }
-        // ---- the recursion: 2 FP ops per entry per level ----
-#pragma unroll
-        for (int m = 0; m < NLEV; ++m) psum[m] = pin[m];
-#pragma unroll
-        for (int j = 0; j < kSW; ++j) {
-            const float dj = d[j];
-#pragma unroll
-            for (int m = NLEV - 1; m >= 1; --m) {
-                const float a_prev = A[m - 1][j];
-                if (m < NLEV - 1) A[m][j] += psum[m];
-                psum[m] = fmaf(dj, a_prev, psum[m]);
-            }
-            if (NLEV > 1) A[0][j] += psum[0];
-            psum[0] += dj;
-        }
-        if (valid) {
-#pragma unroll
-            for (int m = 0; m < NLEV; ++m) ksum[m] += psum[m];
-            if (rho == Lin - 1) {
-                if (l == LP - 1) {
-                    int i, jg;
-                    st_decode_item(p, item, i, jg);
-                    const int j = jg * p.G + q;
-                    if (j < p.n2) {
-                        float* o = p.out + (long long)(p.i_off + i) * p.ldo + p.j_off + j;
-                        o[0] = 1.f;
-#pragma unroll
-                        for (int m = 0; m < NLEV; ++m) o[(long long)(m + 1) * p.out_level_stride] = ksum[m];
-                    }
-                }
-                rho = 0;
-                item += p.NW;
-            } else {
-                ++rho;
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < kSW; ++j) g[j] = gn[j];
-    };
-
-    load_row(g);  // skewed row 0
-    long long T = 0;
-    const long long ramp = (LP - 1) < nsteps ? (LP - 1) : nsteps;
-    for (; T < ramp; ++T) step(std::true_type{}, T);
-    for (; T < total - 1; ++T) step(std::false_type{}, T);
-    for (; T < nsteps; ++T) step(std::true_type{}, T);
+    run_stream_consumer<NLEV>(p.it, ring, fb, eb, wg, lane);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -286,8 +141,10 @@ int launch_sigkern_stream(const float* buf, const StreamGeom& g, long long nitem
     if (!buf || !out || nitems < 1 || rows < 1 || nlev < 1) return fail(GPSIG_E_BADARG, "sigkern_stream: bad sizes");
     if (nlev > kStreamMaxLevels) return fail(GPSIG_E_UNSUPPORTED, "stream path supports num_levels <= %d", kStreamMaxLevels);
     if ((uintptr_t)buf & 127u) return fail(GPSIG_E_ALIGN, "stream buffer must be 128-byte aligned");
-    StParams p;
-    p.buf = buf; p.nitems = nitems; p.SR = g.SR; p.NW = g.NW; p.R = g.R; p.S = g.S;
+    StParams sp;
+    sp.buf = buf; sp.SR = g.SR;
+    StreamItems& p = sp.it;
+    p.nitems = nitems; p.NW = g.NW; p.R = g.R; p.S = g.S;
     p.Lin = rows; p.LP = LP; p.log2LP = ilog2_exact(LP); p.G = 32 / LP;
     p.njg = (n2 + p.G - 1) / p.G;
     p.n1 = n1; p.n2 = n2;
@@ -296,14 +153,14 @@ int launch_sigkern_stream(const float* buf, const StreamGeom& g, long long nitem
     const size_t smem = (size_t)g.ncw * g.S * ((size_t)g.R * kRowBytes + 16);
     ProfScope prof(GPSIG_PROF_RECURSION, st, (double)nitems * p.G);
     switch (nlev) {
-        case 1: return launch_stream_inst<1>(p, g, smem, st);
-        case 2: return launch_stream_inst<2>(p, g, smem, st);
-        case 3: return launch_stream_inst<3>(p, g, smem, st);
-        case 4: return launch_stream_inst<4>(p, g, smem, st);
-        case 5: return launch_stream_inst<5>(p, g, smem, st);
-        case 6: return launch_stream_inst<6>(p, g, smem, st);
-        case 7: return launch_stream_inst<7>(p, g, smem, st);
-        case 8: return launch_stream_inst<8>(p, g, smem, st);
+        case 1: return launch_stream_inst<1>(sp, g, smem, st);
+        case 2: return launch_stream_inst<2>(sp, g, smem, st);
+        case 3: return launch_stream_inst<3>(sp, g, smem, st);
+        case 4: return launch_stream_inst<4>(sp, g, smem, st);
+        case 5: return launch_stream_inst<5>(sp, g, smem, st);
+        case 6: return launch_stream_inst<6>(sp, g, smem, st);
+        case 7: return launch_stream_inst<7>(sp, g, smem, st);
+        case 8: return launch_stream_inst<8>(sp, g, smem, st);
     }
     return fail(GPSIG_E_UNSUPPORTED, "stream path supports num_levels <= %d", kStreamMaxLevels);
 }

@@ -66,8 +66,9 @@ enum {
     GPSIG_PROF_RECURSION = 2,  /* TMA-staged first-order recursion (a4) -- the dominant kernel */
     GPSIG_PROF_RECURSION_OTHER = 3, /* generic first-order and higher-order recursions (a4 fallback, a5) */
     GPSIG_PROF_EPILOGUE = 4,   /* normalise / weight / sum, mirror (a7) */
-    GPSIG_PROF_TENS = 5,       /* inducing-tensor kernels (a9-a11) */
-    GPSIG_PROF_NUM_CLASSES = 6
+    GPSIG_PROF_TENS = 5,       /* inducing-tensor kernels (a9-a11) and low-rank kernels (a15) */
+    GPSIG_PROF_FUSED = 6,      /* fused increment-Gram + recursion kernel (a3 + a4 in one launch, no HBM intermediate) */
+    GPSIG_PROF_NUM_CLASSES = 7
 };
 long long gpsig_launch_count(void);
 int gpsig_profile_enable(int on);

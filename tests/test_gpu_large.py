@@ -164,3 +164,26 @@ def test_kuf_fast_and_generic_paths_vs_oracle(kind, L, d, M, diff):
         k, ko = _pair(kind, L, d, M, lengthscales=1.3 * np.ones(d), difference=diff, normalization=False)
         got = k.K_tens_vs_seq(Z, X, increments=inc, return_levels=True).cpu().numpy()
         assert_levels_close(got, ko.K_tens_vs_seq(Z, X, increments=inc, return_levels=True), msg="Kuf %s inc=%s" % (kind, inc))
+
+
+@pytest.mark.parametrize("kind", ["linear", "rbf"])
+def test_fused_kernel_is_bit_identical_to_the_pipeline(kind, monkeypatch):
+    """The opt-in fused Gram + recursion kernel (fused.cu, GPSIG_FUSED=1) against the default two-kernel path."""
+    X = random_walks(75, 64, 5, 31).reshape(75, -1)
+    Y = random_walks(22, 64, 5, 32).reshape(22, -1)
+    k, _ = _pair(kind, 64, 5, 4, lengthscales=1.4)
+    monkeypatch.delenv("GPSIG_FUSED", raising=False)
+    ref_s, ref_r = k.K(X, return_levels=True).clone(), k.K(X, Y, return_levels=True).clone()
+    monkeypatch.setenv("GPSIG_FUSED", "1")
+    from gpsig_b200 import _lib
+    import ctypes
+    lib = _lib.load()
+    lib.gpsig_profile_reset(); lib.gpsig_profile_enable(1)
+    got_s, got_r = k.K(X, return_levels=True), k.K(X, Y, return_levels=True)
+    torch.cuda.synchronize()
+    lib.gpsig_profile_enable(0)
+    ms, n, un = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
+    lib.gpsig_profile_read(6, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(un))
+    lib.gpsig_profile_reset()
+    assert n.value == 2, "the fused kernel did not run"
+    assert torch.equal(got_s, ref_s) and torch.equal(got_r, ref_r)
