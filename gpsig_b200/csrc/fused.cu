@@ -15,9 +15,12 @@
 //
 // STATUS (round 1): correct and bit-identical to the two-kernel path (tests/test_gpu_large.py), but NOT the default:
 // measured 304 ms (Linear) / 393 ms (RBF) for K(X,X) at N=4096, L=128, d=8, M=5 against 199 / 226 ms for producer +
-// stream recursion.  The recursion is a latency-bound dependency chain per warp (~0.25 IPC each): the stream kernel
-// hides that with 11 consumer warps per SM, here only 4 of the 12 warps consume (the consumer's 158 registers leave no
-// room for more).  The fix is a lighter consumer (8-column strips, ~90 registers, 8+ consumers per SM) -- next round.
+// stream recursion (profiles/r1m_fused_v1.md).  About half of the executed instructions are barrier polling: the
+// consumers wait for rows.  Known costs on the producers' critical path: the per-item column reload (item decode +
+// 16 dependent global loads, staggered over the 8 strips so every warp pays it 8 times per item), the exposed x-tile
+// load at item boundaries, and the sleep-poll handshake; and only 4 of 12 warps run the latency-bound recursion where
+// the stream kernel runs 11.  Next round: prefetch the next item's columns/x tile one item ahead (cp.async), decode once
+// per pair of warps, and a lighter consumer (8-column strips) so that more of them fit.
 // Enable with GPSIG_FUSED=1.
 #include <stdlib.h>
 
