@@ -203,7 +203,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 template <bool RBF, int DPA>
 __global__ void __launch_bounds__(256) delta_producer_fast_kernel(const ProdParams p) {
     extern __shared__ __align__(16) float sA[];  // [rowsA][DPA] of the current row sequence
-    constexpr int H = DPA / 2;
+    constexpr int H = RBF ? DPA / 2 - 1 : DPA / 2;  // float2 pairs that carry data (the last RBF pair is padding)
     constexpr int NPT = RBF ? 5 : 4;
     const int tpp = p.P >> 2;      // threads per pair row
     const int ppb = blockDim.x / tpp;
@@ -228,8 +228,8 @@ __global__ void __launch_bounds__(256) delta_producer_fast_kernel(const ProdPara
 #pragma unroll
         for (int h = 0; h < H; ++h) y[u][h] = ok ? src[h] : make_float2(0.f, 0.f);
         if (RBF) {  // y side of the augmented product: (..., 1, -|y|^2/2)
-            const float2 a = y[u][H - 2];
-            y[u][H - 2] = make_float2(a.y, a.x);
+            const float2 a = y[u][H - 1];
+            y[u][H - 1] = make_float2(a.y, a.x);
         }
     }
     const int group_last_j = (j / p.G) * p.G + p.G - 1;
@@ -260,13 +260,9 @@ __global__ void __launch_bounds__(256) delta_producer_fast_kernel(const ProdPara
         // f[0..3] (and the halo f[4] for RBF) of row s
         auto eval_row = [&](int s, float (&f)[NPT]) {
             float2 x[H];
-            const float4* xs = reinterpret_cast<const float4*>(sA + s * DPA);
+            const float2* xs = reinterpret_cast<const float2*>(sA + s * DPA);
 #pragma unroll
-            for (int h4 = 0; h4 < DPA / 4; ++h4) {
-                const float4 v = xs[h4];
-                x[2 * h4] = make_float2(v.x, v.y);
-                x[2 * h4 + 1] = make_float2(v.z, v.w);
-            }
+            for (int h = 0; h < H; ++h) x[h] = xs[h];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 float2 acc = make_float2(0.f, 0.f);

@@ -187,3 +187,31 @@ def test_fused_kernel_is_bit_identical_to_the_pipeline(kind, monkeypatch):
     lib.gpsig_profile_reset()
     assert n.value == 2, "the fused kernel did not run"
     assert torch.equal(got_s, ref_s) and torch.equal(got_r, ref_r)
+
+
+@pytest.mark.parametrize("kind", ["linear", "rbf"])
+def test_edge_shapes(kind):
+    """one sequence; two-point sequences; one level; ragged pair groups; sequences beyond the 512-column fast path."""
+    for n, L, d, M in ((1, 16, 2, 3), (3, 2, 2, 2), (5, 9, 1, 1), (7, 33, 3, 2), (3, 600, 2, 2)):
+        X = random_walks(n, L, d, 100 + L).reshape(n, -1)
+        k, ko = _pair(kind, L, d, M, lengthscales=1.1)
+        assert_levels_close(k.K(X, return_levels=True).cpu().numpy(), ko.K(X, return_levels=True), msg="symm %s" % ((n, L, d, M),))
+        Y = random_walks(2, L, d, 200 + L).reshape(2, -1)
+        assert_close(k.compute_K(X, Y), ko.K(X, Y), msg="rect %s" % ((n, L, d, M),))
+    # a single time step: no increments at all -> every level >= 1 vanishes, K = variances[0] * sigma (normalised: 0/0 guarded
+    # by the jitter exactly as in the reference)
+    X1 = random_walks(4, 1, 3, 5).reshape(4, -1)
+    k, ko = _pair(kind, 1, 3, 3, normalization=False)
+    assert_close(k.compute_K_symm(X1), ko.K(X1), msg="L=1")
+
+
+def test_unsupported_configurations_raise_instead_of_falling_back():
+    from gpsig_b200 import kernels, _lib
+    X = random_walks(4, 8, 20, 1).reshape(4, -1)
+    k = kernels.SignatureRBF(8 * 20, 20, 3)                      # 20 features: beyond the producers' 16
+    with pytest.raises(_lib.GPSigError):
+        k.K(X)
+    with pytest.raises(ValueError):
+        kernels.SignatureRBF(10, 3, 2)                           # input_dim not a multiple of num_features (kernels.py:98-101)
+    with pytest.raises(NotImplementedError):
+        kernels.SignatureSpectral(8, 2, 2, family="mixed")
