@@ -14,6 +14,7 @@ from . import _lib, settings
 from . import low_rank_calculations as _lr
 from . import signature_algs as _algs
 
+_MAX_FUSED_FEATURES = 16   # widest (lagged) state space of the fused Gram producers (gram.cu)
 _KIND = dict(linear=0, rbf=1, cosine=2, poly=3, mix=4, matern12=5, matern32=6, matern52=7, spectral=8)
 
 
@@ -185,6 +186,8 @@ class SignatureKernel:
         lib = _lib.load()
         dev = X.device
         n1, L1, d = X.shape
+        if d > _MAX_FUSED_FEATURES:
+            return self._K_seq_wide(X, X2, row_blocks)
         n2, L2 = (n1, L1) if X2 is None else (X2.shape[0], X2.shape[1])
         blocks = [(0, n1)] if row_blocks is None else list(row_blocks)
         nrows = sum(e - b for b, e in blocks)
@@ -204,11 +207,43 @@ class SignatureKernel:
                 row0 += e - b
         return out
 
+    def _K_seq_wide(self, X, X2=None, row_blocks=None):
+        """_K_seq for state spaces wider than the fused producers handle (d > 16, e.g. RNN features): the static-kernel
+        Gram of a row block is materialised exactly as kernels.py:225-230 does (gpsig_gram) and handed to the
+        operator-level recursion (gpsig_sigkern_levels, differencing fused).  Functional fallback, not the tuned path."""
+        n1, L1, d = X.shape
+        Xs = self._scale_tens(X)
+        X2s = Xs if X2 is None else self._scale_tens(X2)
+        n2, L2 = X2s.shape[0], X2s.shape[1]
+        flat2 = X2s.reshape(n2 * L2, d)
+        blocks = [(0, n1)] if row_blocks is None else list(row_blocks)
+        rows_per = max(1, int((1 << 30) // max(1, 4 * L1 * n2 * L2)))
+        outs = []
+        for b, e in blocks:
+            for c0 in range(b, e, rows_per):
+                c1 = min(e, c0 + rows_per)
+                M = self._base_gram(Xs[c0:c1].reshape((c1 - c0) * L1, d), flat2).reshape(c1 - c0, L1, n2, L2)
+                outs.append(_algs._sigkern(M, self.num_levels, self.order, self.difference))
+        return torch.cat(outs, dim=1).contiguous()
+
+    def _K_seq_diag_wide(self, X):
+        n, L, d = X.shape
+        Xs = self._scale_tens(X)
+        outs = []
+        for c0 in range(0, n, 8):
+            c = min(8, n - c0)
+            M = self._base_gram(Xs[c0:c0 + c].reshape(c * L, d)).reshape(c, L, c, L)
+            idx = torch.arange(c, device=X.device)
+            outs.append(_algs._sigkern(M[idx, :, idx, :].contiguous(), self.num_levels, self.order, self.difference))
+        return torch.cat(outs, dim=1).contiguous()
+
     def _K_seq_diag(self, X):
         """kernels.py:188-205; returns (M+1, N)."""
         lib = _lib.load()
         dev = X.device
         n, L, d = X.shape
+        if d > _MAX_FUSED_FEATURES:
+            return self._K_seq_diag_wide(X)
         out = torch.empty((self.num_levels + 1, n), device=dev, dtype=torch.float32)
         ws = self._workspace(dev, min(n, 64), L, min(n, 64), L, d)
         inv_ls = self._inv_ls(dev)

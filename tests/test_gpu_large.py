@@ -207,11 +207,23 @@ def test_edge_shapes(kind):
 
 def test_unsupported_configurations_raise_instead_of_falling_back():
     from gpsig_b200 import kernels, _lib
-    X = random_walks(4, 8, 20, 1).reshape(4, -1)
-    k = kernels.SignatureRBF(8 * 20, 20, 3)                      # 20 features: beyond the producers' 16
-    with pytest.raises(_lib.GPSigError):
-        k.K(X)
     with pytest.raises(ValueError):
         kernels.SignatureRBF(10, 3, 2)                           # input_dim not a multiple of num_features (kernels.py:98-101)
     with pytest.raises(NotImplementedError):
         kernels.SignatureSpectral(8, 2, 2, family="mixed")
+
+
+@pytest.mark.parametrize("kind", ["linear", "rbf"])
+def test_wide_state_space_falls_back_to_the_materialised_gram(kind):
+    """d = 24 (> 16): Gram blocks through gpsig_gram + the operator-level recursion; same results, slower path."""
+    n, L, d, M = 9, 32, 24, 3
+    X = random_walks(n, L, d, 77).reshape(n, -1)
+    Y = random_walks(4, L, d, 78).reshape(4, -1)
+    k, ko = _pair(kind, L, d, M, lengthscales=float(np.sqrt(d)))
+    assert_levels_close(k.K(X, return_levels=True).cpu().numpy(), ko.K(X, return_levels=True), msg="symm")
+    assert_close(k.compute_K(X, Y), ko.K(X, Y), msg="rect")
+    rng = np.random.default_rng(3)
+    Z = 0.3 * rng.standard_normal((6, 5, 2, d))
+    r, ro = k.K_tens_n_seq_covs(Z, X, increments=True), ko.K_tens_n_seq_covs(Z, X, increments=True)
+    for a, b, nm in zip(r, ro, ("zz", "zx", "xx")):
+        assert_close(a.cpu().numpy(), b, msg=nm)
