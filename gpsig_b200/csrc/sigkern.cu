@@ -39,6 +39,7 @@ struct FoParams {
                        // by the output address: out[(i_off + i) * ldo + j_off + j]
     long long ldo;
     int nstages;
+    int log2R;      // Gram rows per TMA box (1 or 2): one bulk-tensor copy per box, one mbarrier per box
     int slot_j, slot_s, slot_i;  // tensor-map coordinate slots (2..4), dims sorted by stride
     float* out;
     long long out_level_stride;
@@ -108,16 +109,18 @@ sigkern_fo_tma_kernel(const __grid_constant__ CUtensorMap tmap, const FoParams p
         c[p.slot_j] = prod_jg * p.G;
         c[p.slot_s] = prod_rho;
         c[p.slot_i] = prod_i;
-        const uint32_t bar = bars_u + 8 * prod_stage;
-        mbar_arrive_expect_tx(bar, kStageBytes);
+        const uint32_t bar = bars_u + 8 * (prod_stage >> p.log2R);
+        mbar_arrive_expect_tx(bar, kStageBytes << p.log2R);
         tma_load_5d(ring_u + prod_stage * kStageBytes, &tmap, bar, c[0], c[1], c[2], c[3], c[4]);
         ++prod_seq;
-        if (++prod_rho == Lin) { prod_rho = 0; prod_item += NW; }
-        if (++prod_stage == S) prod_stage = 0;
+        prod_rho += 1 << p.log2R;  // Lin is a multiple of the box height
+        if (prod_rho == Lin) { prod_rho = 0; prod_item += NW; }
+        prod_stage += 1 << p.log2R;
+        if (prod_stage == S) prod_stage = 0;
     };
     if (lane == 0) {
         const long long pre = total < S ? total : S;
-        for (long long n = 0; n < pre; ++n) issue();
+        for (long long n = 0; n < pre; n += 1 << p.log2R) issue();
     }
 
     // ---- consumer state (per lane) ----
@@ -153,7 +156,7 @@ sigkern_fo_tma_kernel(const __grid_constant__ CUtensorMap tmap, const FoParams p
         for (int j = 0; j < kW; ++j) d[j] = 0.f;
         bool first_row = false;
         if (valid) {
-            mbar_wait(bars_u + 8 * stage, phase);
+            mbar_wait(bars_u + 8 * (stage >> p.log2R), phase);
             const uint32_t base = ring_u + stage * kStageBytes;
             float g[kW + 1];
 #pragma unroll
@@ -182,7 +185,11 @@ sigkern_fo_tma_kernel(const __grid_constant__ CUtensorMap tmap, const FoParams p
         // the row consumed by the last strip lanes in this step is free in all pair groups: refill its stage
         if (lane == 0) {
             const long long freed = T - (LP - 1);
-            if (freed >= 0 && freed + S < total) issue();
+            if (p.log2R == 0) {
+                if (freed >= 0 && freed + S < total) issue();
+            } else if (freed >= 1 && (freed & 1) && freed - 1 + S < total) {
+                issue();  // both rows of the box are free
+            }
         }
         if (valid && first_row) {
 #pragma unroll
@@ -488,10 +495,18 @@ int launch_sigkern_fo(const float* M, int n1, int Lrows, int n2, int ncols, int 
         int S = p.LP + pf;
         // spend leftover shared memory on a deeper prefetch (bounded)
         while (S < p.LP + 12 && (size_t)nwarps * (S + 1) * (kStageBytes + 8) <= (size_t)max_smem && nwarps < kMaxWarps) ++S;
+        // two Gram rows per TMA box when the rows of a pair group are adjacent in the box (stride_s > stride_j) and
+        // items hold an even number of rows: halves the bulk-tensor copies, whose issue rate (~1 per 100 cycles per SM)
+        // is what limits this kernel (tools/ubench/tma_stream.cu)
+        p.log2R = (Lrows % 2 == 0 && ss > sj && n1 > 1) ? 1 : 0;
+        if (p.log2R) {
+            if (S & 1) ++S;
+            while ((size_t)nwarps * S * (kStageBytes + 8) > (size_t)max_smem) S -= 2;
+        }
         p.nstages = S;
         // tensor map: dims (32, pitch/32, .., .., ..) with (j, s, i) ordered by ascending stride
         struct Dim { long long stride; uint64_t size; uint32_t box; int which; };
-        Dim dj{sj, (uint64_t)n2, (uint32_t)p.G, 0}, ds{ss, (uint64_t)Lrows, 1u, 1}, di{si, (uint64_t)n1, 1u, 2};
+        Dim dj{sj, (uint64_t)n2, (uint32_t)p.G, 0}, ds{ss, (uint64_t)Lrows, 1u << p.log2R, 1}, di{si, (uint64_t)n1, 1u, 2};
         if (n1 == 1) di.stride = (long long)1 << 38;  // never dereferenced beyond coordinate 0; keep it the largest
         Dim order[3] = {dj, ds, di};
         for (int a = 0; a < 3; ++a)

@@ -116,6 +116,24 @@ def cfg5(args):
                       "elbo_relerr_vs_oracle_subproblem": abs(got - ref) / abs(ref)}), flush=True)
 
 
+def op(args):
+    """operator level: gpsig_sigkern_levels on a caller-supplied Gram tensor [n1, L, n2, L] (the tensor-map TMA kernel)."""
+    from gpsig_b200 import signature_algs as S
+    n1, n2, L, M = int(30 * args.scale) or 1, 4096, 128, 5
+    G = torch.randn((n1, L, n2, L), device="cuda", dtype=torch.float32) * 0.05
+    for diff in (True, False):
+        ms, prof = timed(lambda: S.signature_kern_first_order(G, M, difference=diff), args.steps)
+        r = prof.get("recursion", {"ms_per_call": ms})
+        gb = n1 * n2 * (4.0 * L * L + 4 * (M + 1)) / 1e9
+        # parity of a corner against the oracle
+        got = S.signature_kern_first_order(G[:2, :, :6, :].contiguous(), M, difference=diff).cpu().numpy()
+        ref = O.signature_kern_first_order(G[:2, :, :6, :].cpu().numpy().astype(np.float64), M, difference=diff)
+        print(json.dumps({"config": "operator signature_kern_first_order M[%d,%d,%d,%d] levels=%d difference=%s" % (n1, L, n2, L, M, diff),
+                          "ms": ms, "kernel_ms": r["ms_per_call"], "GBps": gb / (r["ms_per_call"] * 1e-3),
+                          "frac_of_6550": gb / (r["ms_per_call"] * 1e-3) / 6550.4,
+                          "relerr_vs_oracle_corner": max(relerr(got[m], ref[m]) for m in range(1, M + 1))}), flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--cfg", default="all")
@@ -126,3 +144,5 @@ if __name__ == "__main__":
         cfg3(a)
     if a.cfg in ("cfg5", "all"):
         cfg5(a)
+    if a.cfg in ("op", "all"):
+        op(a)
