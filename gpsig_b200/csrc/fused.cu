@@ -14,13 +14,15 @@
 //   empty[c][s] : count 1 -- the consumer has read the stage
 //
 // STATUS (round 1): correct and bit-identical to the two-kernel path (tests/test_gpu_large.py), but NOT the default:
-// measured 304 ms (Linear) / 393 ms (RBF) for K(X,X) at N=4096, L=128, d=8, M=5 against 199 / 226 ms for producer +
-// stream recursion (profiles/r1m_fused_v1.md).  About half of the executed instructions are barrier polling: the
-// consumers wait for rows.  Known costs on the producers' critical path: the per-item column reload (item decode +
-// 16 dependent global loads, staggered over the 8 strips so every warp pays it 8 times per item), the exposed x-tile
-// load at item boundaries, and the sleep-poll handshake; and only 4 of 12 warps run the latency-bound recursion where
-// the stream kernel runs 11.  Next round: prefetch the next item's columns/x tile one item ahead (cp.async), decode once
-// per pair of warps, and a lighter consumer (8-column strips) so that more of them fit.
+// measured 304 ms (Linear) / 393 ms (RBF) for K(X,X) at N=4096, L=128, d=8, M=5 against 190-210 / 202-226 ms for
+// producer + stream recursion.  ncu (profiles/r1p_fused_v2.md): ~840 warp instructions per stream row where the work
+// needs ~400 (consumer 197, two producer warps 201); the rest is the producers' sleep-poll on the empty barriers (228:
+// they are far ahead and idle) and the per-item decode (98: 64-bit divisions inside the binary search, run by every
+// strip).  The real limit is the CONSUMER: one recursion warp issues an instruction only every ~4 cycles (dependent
+// FADD/FFMA chains, ~0.27 IPC); the stream kernel hides that with 11 consumer warps per SM, here only 4 of the 12 warps
+// consume because a consumer needs 158 registers.  Next round: 8-column strips (A_m state 32 instead of 64 registers
+// -> ~95 registers -> 10-12 consumers per SM), try_wait with a suspend hint instead of sleep-polling, decode once
+// per warp pair, prefetch of the next item's columns / x tile.
 // Enable with GPSIG_FUSED=1.
 #include <stdlib.h>
 
