@@ -14,15 +14,13 @@
 //   empty[c][s] : count 1 -- the consumer has read the stage
 //
 // STATUS (round 1): correct and bit-identical to the two-kernel path (tests/test_gpu_large.py), but NOT the default:
-// measured 304 ms (Linear) / 393 ms (RBF) for K(X,X) at N=4096, L=128, d=8, M=5 against 190-210 / 202-226 ms for
-// producer + stream recursion.  ncu (profiles/r1p_fused_v2.md): ~840 warp instructions per stream row where the work
-// needs ~400 (consumer 197, two producer warps 201); the rest is the producers' sleep-poll on the empty barriers (228:
-// they are far ahead and idle) and the per-item decode (98: 64-bit divisions inside the binary search, run by every
-// strip).  The real limit is the CONSUMER: one recursion warp issues an instruction only every ~4 cycles (dependent
-// FADD/FFMA chains, ~0.27 IPC); the stream kernel hides that with 11 consumer warps per SM, here only 4 of the 12 warps
-// consume because a consumer needs 158 registers.  Next round: 8-column strips (A_m state 32 instead of 64 registers
-// -> ~95 registers -> 10-12 consumers per SM), try_wait with a suspend hint instead of sleep-polling, decode once
-// per warp pair, prefetch of the next item's columns / x tile.
+// measured 222 ms (Linear) / 287 ms (RBF) for K(X,X) at N=4096, L=128, d=8, M=5 against 190-210 / 202-226 ms for
+// producer + stream recursion (first version: 304 / 393 ms, profiles/r1m_fused_v1.md, r1p_fused_v2.md -- sleep-polling
+// producers and a 64-bit-division item decode per strip cost 40 % of the issued instructions; both are gone).
+// With the producers' arithmetic switched off (GPSIG_FUSED_DBG=1) the kernel still takes 181 / 208 ms: the bound is the
+// consumer side -- 4 recursion warps per SM where the stream kernel runs 11 (a consumer needs 158 registers), each
+// waiting on a two-warp handshake every 4 rows.  Next round: 8-column strips (A_m state 32 instead of 64 registers
+// -> ~95 registers -> 10-12 consumers per SM) and prefetch of the next item's columns / x tile.
 // Enable with GPSIG_FUSED=1.
 #include <stdlib.h>
 
@@ -39,6 +37,7 @@ struct FusedParams {
     const float* B;   // prepared column-side points / increments (n2_total, rowsB, DPA)
     int rowsA, rowsB; // == stream rows per item (RBF: the first row only primes the differencing and emits zeros)
     int P;            // padded columns per pair (16 LP)
+    int dbg;          // experiments only: 1 = producers skip the arithmetic (stores zeros)
     StreamItems it;   // it.Lin == rowsA
 };
 
@@ -111,6 +110,27 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) sigkern_fused_kernel(cons
 #pragma unroll
         for (int h = 0; h < HU; ++h) y[u][h] = make_float2(0.f, 0.f);
     }
+    // (i, jg) of an item of this stream, advanced item by item (u -> u + NW) without divisions: `rel` is the position of the
+    // group inside the groups row i keeps (all of them, or those right of the diagonal for symmetric K)
+    struct Track { int i, rel, cnt; };
+    auto track_init = [&](Track& t, long long u) {
+        int jg;
+        st_decode_item(it, u, t.i, jg);
+        const int fg = first_group(t.i, it.G, it.upper_only, it.i_off, it.j_off);
+        t.rel = jg - fg;
+        t.cnt = it.njg - fg;
+    };
+    auto track_next = [&](Track& t) {
+        t.rel += it.NW;
+        while (t.rel >= t.cnt && t.i + 1 < it.n1) {
+            t.rel -= t.cnt;
+            ++t.i;
+            t.cnt = it.njg - first_group(t.i, it.G, it.upper_only, it.i_off, it.j_off);
+        }
+    };
+    Track tx, ty;        // item whose row sequence is staged next / item this strip works on
+    track_init(tx, wg);
+    ty = tx;
     int s = -l;          // row of the current item (negative: the strip has not started yet)
     long long m = 0;     // index of the current item inside the stream
     int stage = 0, srow = 0, round = 0;
@@ -119,8 +139,8 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) sigkern_fused_kernel(cons
     for (long long sg = 0; sg < nsteps; ++sg) {
         // ---- the pair stages the row sequence of item (sg / Lrow) when strip 0 reaches it ----
         if (s0 == 0 && sg < total) {
-            int i, jg;
-            st_decode_item(it, wg + mi * it.NW, i, jg);
+            const int i = tx.i;
+            track_next(tx);
             const float4* src = reinterpret_cast<const float4*>(p.A + (long long)(it.i_off + i) * p.rowsA * DPA);
             const uint32_t dst = xb + (uint32_t)(mi & 1) * xbytes;
             for (int e = pt; e < p.rowsA * (DPA / 4); e += 64) {
@@ -132,16 +152,14 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) sigkern_fused_kernel(cons
         }
         // ---- entering a ring stage: wait until the consumer has handed it back ----
         if (srow == 0 && round > 0) {
-            if (lane == 0) {
-                while (!mbar_test_wait(eb + 8 * stage, (uint32_t)(round + 1) & 1u)) __nanosleep(64);
-            }
+            if (lane == 0) mbar_wait(eb + 8 * stage, (uint32_t)(round + 1) & 1u);  // try_wait suspends in hardware
             __syncwarp();
         }
         const bool valid = s >= 0 && (sg - l) < total;
         // ---- this strip starts a new item: its column points move into registers ----
         if (valid && s == 0) {
-            int i, jg;
-            st_decode_item(it, wg + m * it.NW, i, jg);
+            const int jg = ty.rel + first_group(ty.i, it.G, it.upper_only, it.i_off, it.j_off);
+            track_next(ty);
             int jl = jg * it.G + q;
             if (jl > it.n2 - 1) jl = it.n2 - 1;  // padding pair of a ragged last group: any valid sequence will do
             const long long j = (long long)it.j_off + jl;
@@ -162,7 +180,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) sigkern_fused_kernel(cons
         float o[kFusedCols];
 #pragma unroll
         for (int u = 0; u < kFusedCols; ++u) o[u] = 0.f;
-        if (valid) {
+        if (valid && p.dbg != 1) {
             const float* xs = xgen + (size_t)(m & 1) * (xbytes >> 2) + (size_t)s * DPA;
             float2 x[HU];
 #pragma unroll
@@ -255,9 +273,18 @@ int launch_sigkern_fused(bool rbf, const float* A, const float* B, int rowsA, in
     if (!A || !B || !out || nitems < 1 || rowsA < 1 || rowsB < 1) return fail(GPSIG_E_BADARG, "sigkern_fused: bad sizes");
     FusedParams p;
     p.A = A; p.B = B; p.rowsA = rowsA; p.rowsB = rowsB; p.P = P;
+    { const char* dv = getenv("GPSIG_FUSED_DBG"); p.dbg = (dv && *dv) ? atoi(dv) : 0; }
     StreamItems& it = p.it;
     it.nitems = nitems;
     it.R = 4; it.S = 3;
+    {   // tuning knobs for experiments
+        const char* r = getenv("GPSIG_FUSED_R");
+        const char* ss = getenv("GPSIG_FUSED_S");
+        if (r && *r) it.R = atoi(r);
+        if (ss && *ss) it.S = atoi(ss);
+        if (it.R < 1) it.R = 1;
+        if (it.S < 2) it.S = 2;
+    }
     it.Lin = rowsA; it.LP = LP; it.log2LP = flog2(LP); it.G = 32 / LP;
     it.njg = (n2 + it.G - 1) / it.G;
     it.n1 = n1; it.n2 = n2;
