@@ -123,3 +123,89 @@ def sharded_K(kern, X, X2=None, group=None, blocks_per_rank=8):
     Xr = X[torch.as_tensor(rows, device=X.device)] if isinstance(X, torch.Tensor) else X[rows]
     local = kern.K(Xr, X2) if len(rows) else torch.zeros((0, X2.shape[0]), device=kern._dev(), dtype=torch.float32)
     return gather_rows(local, n, parts, group)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Inducing-tensor covariances and the SVGP bound: shard the SEQUENCE axis.  Kzz is tiny and replicated;
+# every (z, n) entry of Kzx depends on one inducing tensor and one sequence only, so the column shards are independent
+# and one all-gather assembles Kzx; the ELBO needs one all-reduce of a scalar.
+# ----------------------------------------------------------------------------------------------------------------------
+def column_shards(n, world_size):
+    """contiguous [begin, end) of the sequence axis per rank (sizes differ by at most one)."""
+    base, rem = divmod(n, world_size)
+    out, b = [], 0
+    for r in range(world_size):
+        e = b + base + (1 if r < rem else 0)
+        out.append((b, e))
+        b = e
+    return out
+
+
+def _world(group):
+    if dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+def gather_columns(local, shards, group=None):
+    """All-gather column shards (rank r holds (rows, e_r - b_r)) into (rows, n) with ONE collective."""
+    ws = len(shards)
+    if ws == 1:
+        return local
+    width = max(e - b for b, e in shards)
+    rows = local.shape[0]
+    padded = torch.zeros((width, rows), device=local.device, dtype=local.dtype)
+    padded[:local.shape[1]] = local.transpose(0, 1)
+    if dist.get_backend(group) == "nccl":
+        gathered = torch.empty((ws, width, rows), device=local.device, dtype=local.dtype)
+        dist.all_gather_into_tensor(gathered, padded, group=group)
+    else:
+        host = padded.cpu()
+        chunks = [torch.empty_like(host) for _ in range(ws)]
+        dist.all_gather(chunks, host, group=group)
+        gathered = torch.stack(chunks).to(local.device)
+    return torch.cat([gathered[r, :e - b].transpose(0, 1) for r, (b, e) in enumerate(shards)], dim=1).contiguous()
+
+
+def sharded_K_tens_vs_seq(kern, Z, X, increments=False, group=None):
+    """Kuf = kern.K_tens_vs_seq(Z, X) (kernels.py:538-588) with the sequences sharded over the ranks; full (nz, N) on every
+    rank; equal to the single-GPU result up to rounding (the RBF path centres the points on the first sequence of the call;
+    exact mode only -- the low-rank mode draws per call and is not sharded)."""
+    ws, rk = _world(group)
+    shards = column_shards(X.shape[0], ws)
+    b, e = shards[rk]
+    nz = Z.shape[1]
+    if e > b:
+        local = kern.K_tens_vs_seq(Z, X[b:e], increments=increments)
+    else:
+        local = torch.zeros((nz, 0), device=kern._dev(), dtype=torch.float32)
+    return gather_columns(local, shards, group)
+
+
+def sharded_elbo(model, X=None, Y=None, group=None):
+    """SVGP bound (models.py:39-59) data-parallel over the sequences: every rank evaluates Kuu_Kuf_Kff, the conditional and
+    the variational expectations of ITS shard, the partial sums are all-reduced (one scalar), the KL term is replicated."""
+    from . import models as _models
+    ws, rk = _world(group)
+    X = model.X if X is None else X
+    Y = model.Y if Y is None else Y
+    n = X.shape[0]
+    b, e = column_shards(n, ws)[rk]
+    if model.whiten:
+        f_mean, f_var = model._build_predict(X[b:e])
+        Kzz = None
+    else:
+        f_mean, f_var, Kzz = model._build_predict(X[b:e], return_Kzz=True)
+    dev = f_mean.device
+    q_sqrt = model._dev(model.q_sqrt, dev)
+    KL = _models.gauss_kl(model._dev(model.q_mu, dev), torch.tril(q_sqrt) if q_sqrt.dim() == 3 else q_sqrt, K=Kzz)
+    part = torch.sum(model.likelihood.variational_expectations(f_mean, f_var, model._dev(Y[b:e], dev))).reshape(1).double()
+    if ws > 1:
+        if dist.get_backend(group) == "nccl":
+            dist.all_reduce(part, group=group)
+        else:
+            host = part.cpu()
+            dist.all_reduce(host, group=group)
+            part = host.to(dev)
+    scale = float(model.num_data) / float(n)
+    return part[0].to(torch.float32) * scale - KL

@@ -51,7 +51,23 @@ def _worker(rank, ws, port, q):
     k = _kernel()
     K = parallel.sharded_K_symm(k, X)
     ref = k.K(X)
-    q.put((rank, bool(torch.equal(K, ref)), backend))
+    ok = bool(torch.equal(K, ref))
+    # rectangular block, Kuf column shards and the data-parallel ELBO
+    Y2 = random_walks(37, 64, 4, 12).reshape(37, -1)
+    # the RBF path centres the points on the first sequence of each call (translation invariance), so row / column
+    # shards of a rectangular problem agree with the single call to rounding, not bit for bit
+    close = lambda a, b: bool(torch.allclose(a, b, rtol=0, atol=3e-6 * float(b.abs().max())))  # noqa: E731
+    ok = ok and close(parallel.sharded_K(k, X, Y2), k.K(X, Y2))
+    rng = np.random.default_rng(5)
+    Z = 0.4 * rng.standard_normal((10, 9, 2, 4))
+    ok = ok and close(parallel.sharded_K_tens_vs_seq(k, Z, X, increments=True), k.K_tens_vs_seq(Z, X, increments=True))
+    from gpsig_b200 import models, inducing_variables as iv
+    Yl = (rng.standard_normal((150, 1)) > 0).astype(np.float64)
+    m = models.SVGP(X, Yl, k, models.Bernoulli(), iv.InducingTensors(Z, 4, increments=True), num_latent=1,
+                    q_mu=0.2 * rng.standard_normal((9, 1)))
+    e1, e2 = float(parallel.sharded_elbo(m).item()), m.compute_log_likelihood()
+    ok = ok and abs(e1 - e2) < 1e-4 * abs(e2)
+    q.put((rank, ok, backend))
     dist.barrier()
     dist.destroy_process_group()
 

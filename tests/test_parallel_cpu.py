@@ -54,3 +54,39 @@ def test_gather_rows_gloo_world_size_2(n, n2):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+@pytest.mark.parametrize("n,ws", [(4096, 8), (10, 3), (2, 4), (0, 2)])
+def test_column_shards_cover_the_sequence_axis(n, ws):
+    sh = P.column_shards(n, ws)
+    assert len(sh) == ws and sh[0][0] == 0 and sh[-1][1] == n
+    assert all(a[1] == b[0] for a, b in zip(sh, sh[1:]))
+    sizes = [e - b for b, e in sh]
+    assert max(sizes) - min(sizes) <= 1
+
+
+def _gather_cols_worker(rank, ws, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    n, rows = 11, 3
+    full = torch.arange(rows * n, dtype=torch.float32).reshape(rows, n)
+    sh = P.column_shards(n, ws)
+    b, e = sh[rank]
+    got = P.gather_columns(full[:, b:e].contiguous(), sh)
+    q.put((rank, bool(torch.equal(got, full))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_columns_world_size_2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_cols_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)], res
