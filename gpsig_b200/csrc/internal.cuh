@@ -118,6 +118,11 @@ int launch_sigkern_fo(const float* M, int n1, int Lrows, int n2, int ncols, int 
 int launch_sigkern_stream(const float* buf, const StreamGeom& g, long long nitems, int n1, int n2, int rows, int LP, int nlev,
                           int upper_only, int i_off, int j_off, long long ldo, long long lvl_stride, float* out,
                           cudaStream_t st);
+// Warp-autonomous fused Gram + recursion (warpfused.cu): every warp computes and consumes its own increment rows.
+bool warpfused_supported(bool rbf, int d, int nlev, int ncols, int rowsA);
+int launch_sigkern_warpfused(bool rbf, const float* A, const float* B, int rowsA, int rowsB, int DPA, int ncols, int n1,
+                             int n2_total, int nlev, int upper_only, int i_off, long long ldo, long long lvl_stride, float* out,
+                             cudaStream_t st);
 // Fused Gram + recursion (fused.cu): level stacks straight from prepared points, no chunk buffer.
 bool fused_supported(bool rbf, int d, int nlev, int LP, int rowsA);
 int launch_sigkern_fused(bool rbf, const float* A, const float* B, int rowsA, int rowsB, int d, int DPA, int P, int LP,

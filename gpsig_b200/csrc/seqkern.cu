@@ -192,6 +192,20 @@ extern "C" int gpsig_seq_kern_levels(int kind, const float* params, const float*
     const bool use_ho = order > 1;
     const bool upper = symmetric;
     const bool use_stream = pl.fast && !use_ho && num_levels <= 8;
+    // warp-fused path: every warp computes and consumes its own increment rows (no chunk buffer, no HBM intermediate)
+    if (use_stream && pl.fast_prod && warpfused_supported(kind == GPSIG_KERN_RBF, d, num_levels, pl.ncols, pl.rowsA)) {
+        rc = launch_sigkern_warpfused(kind == GPSIG_KERN_RBF, A, B, pl.rowsA, pl.rowsB, pl.DP, pl.ncols, row_end - row_begin, n2,
+                                      num_levels, upper ? 1 : 0, row_begin, n2, per_level, out_base, st);
+        if (rc != GPSIG_E_UNSUPPORTED) {
+            if (rc) return rc;
+            if (mirror && n1 > 1) {
+                ProfScope prof(GPSIG_PROF_EPILOGUE, st, (double)per_level * nl);
+                mirror_upper_kernel<<<grid_for(per_level * nl, 256), 256, 0, st>>>(out_levels, n1, nl);
+                rc = check_launch();
+            }
+            return rc;
+        }
+    }
     // fused path: the increment Gram never leaves the SM (no chunk buffer, one launch for the whole row range)
     if (use_stream && pl.fast_prod && fused_supported(kind == GPSIG_KERN_RBF, d, num_levels, pl.LP, pl.rowsA)) {
         const int j_off = upper ? (row_begin / pl.G) * pl.G : 0;
