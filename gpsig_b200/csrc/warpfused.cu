@@ -4,7 +4,8 @@
 //
 // One persistent CTA per SM; each warp owns an independent stream of work items.  An item is G = 32 / LP neighbouring
 // pairs (i, j0..j0+G-1); LP lanes cooperate on one pair and lane l owns the 8-COLUMN strip t in [8 l, 8 l + 8): its 8
-// (RBF: 9, the halo) points of the column sequence y_j live in registers for the whole item, A_m[s, t] of all levels
+// points of the column sequence y_j live in registers for the whole item (RBF: the strip of increment columns is shifted
+// left by one so that the halo value comes from lane l - 1, which is one row AHEAD in the skew), A_m[s, t] of all levels
 // too (32 registers at M = 5 -- half of the 16-column strips of sigstream.cu, which is what lets the Gram arithmetic
 // fit beside the recursion).  Lanes run skewed by one row exactly as in sigstream.cu: at step T lane l evaluates the
 // increments Delta[T - l, strip l] (packed fma.rn.f32x2 dot products against the row point x_i[T - l] read from the
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_warpfused_kernel(const W
     extern __shared__ __align__(16) float wsm[];
     constexpr int NA = NLEV > 1 ? NLEV - 1 : 1;
     constexpr int W = kWfCols;
-    constexpr int NPT = RBF ? W + 1 : W;
+    constexpr int NPT = W;
     const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Lrow = p.rowsA, LP = p.LP;
     const long long wg = (long long)blockIdx.x * nwarps + warp;
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_warpfused_kernel(const W
     float psum[NLEV], ksum[NLEV];
     float2 y[NPT][HU];
     float fprev[NPT];
+    float f7 = 0.f, flprev = 0.f;  // RBF: this lane's last column value of the previous step / left-halo value of the previous row
 #pragma unroll
     for (int m = 0; m < NLEV; ++m) { psum[m] = 0.f; ksum[m] = 0.f; }
 #pragma unroll
@@ -170,6 +172,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_warpfused_kernel(const W
             pin[m] = __shfl_up_sync(0xffffffffu, psum[m], 1);
             if (l == 0) pin[m] = 0.f;
         }
+        float fl = 0.f;
+        if (RBF) fl = __shfl_up_sync(0xffffffffu, f7, 1);
         // ---- increments of row s of the strip ----
         float d[W];
 #pragma unroll
@@ -189,12 +193,17 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_warpfused_kernel(const W
                 f[u] = RBF ? wf_ex2(v) : v;
             }
             if (RBF) {
+                // lane l owns the increment columns 8 l - 1 .. 8 l + 6 (column -1 is a zero pad): the value to the LEFT of
+                // its first point belongs to lane l - 1, which evaluated this very row one step ago
                 if (s > 0) {
+                    d[0] = l == 0 ? 0.f : (f[0] - fl) - (fprev[0] - flprev);
 #pragma unroll
-                    for (int u = 0; u < W; ++u) d[u] = (f[u + 1] - f[u]) - (fprev[u + 1] - fprev[u]);
+                    for (int u = 1; u < W; ++u) d[u] = (f[u] - f[u - 1]) - (fprev[u] - fprev[u - 1]);
                 }
 #pragma unroll
                 for (int u = 0; u < NPT; ++u) fprev[u] = f[u];
+                flprev = fl;
+                f7 = f[W - 1];
             } else {
 #pragma unroll
                 for (int u = 0; u < W; ++u) d[u] = f[u];
@@ -255,17 +264,20 @@ int wf_lanes_per_pair(int ncols) {
     return 1 << wf_log2(need < 2 ? 2 : need);
 }
 
+// Default for LINEAR (measured 153 ms against 190-210 ms for producer + stream recursion on the headline shape).  RBF needs
+// ~230 registers, which leaves 8 warps per SM: 231 ms against 202-226 ms for the two-kernel path, so RBF only takes this
+// path on request (GPSIG_WARPFUSED=1).  GPSIG_WARPFUSED=0 disables it altogether.
 bool warpfused_supported(bool rbf, int d, int nlev, int ncols, int rowsA) {
-    (void)rbf;
     if (nlev < 2 || nlev > 5 || d > 8) return false;
-    if (ncols > 32 * kWfCols || rowsA < 48) return false;
+    if (ncols + 1 > 32 * kWfCols || rowsA < 48) return false;
     const char* v = getenv("GPSIG_WARPFUSED");
-    return !(v && *v == '0');
+    if (v && *v == '0') return false;
+    if (rbf) return v && *v == '1';
+    return true;
 }
 
-template <bool RBF, int NLEV, int DPA, int HU>
-static int launch_wf_inst(WfParams& p, cudaStream_t st) {
-    constexpr int MAXW = RBF ? 8 : 12;  // register budget: 255 / 168 per thread (allocation granule: 4 warps)
+template <bool RBF, int NLEV, int DPA, int HU, int MAXW>
+static int launch_wf_maxw(WfParams& p, cudaStream_t st) {
     auto kern = sigkern_warpfused_kernel<RBF, NLEV, DPA, HU, MAXW>;
     const size_t per_warp = (size_t)(2 * p.xfloats + p.yfloats) * sizeof(float);
     int nw = MAXW;
@@ -284,6 +296,17 @@ static int launch_wf_inst(WfParams& p, cudaStream_t st) {
     ProfScope prof(GPSIG_PROF_FUSED, st, (double)p.nitems * p.G);
     kern<<<grid, nw * 32, smem, st>>>(p);
     return check_launch();
+}
+
+// register budget per thread: 12 warps -> 168, 8 warps -> 255 (allocation granule: 4 warps).  LINEAR fits 168; RBF needs
+// ~230 (8 more points' worth of exponent arguments and the previous row's values), so it runs 8 warps unless
+// GPSIG_WARPFUSED_RBF12=1 asks for the spilling 12-warp build (experiment knob)
+template <bool RBF, int NLEV, int DPA, int HU>
+static int launch_wf_inst(WfParams& p, cudaStream_t st) {
+    if (!RBF) return launch_wf_maxw<RBF, NLEV, DPA, HU, 12>(p, st);
+    const char* v = getenv("GPSIG_WARPFUSED_RBF12");
+    if (v && *v == '1') return launch_wf_maxw<RBF, NLEV, DPA, HU, RBF ? 12 : 8>(p, st);
+    return launch_wf_maxw<RBF, NLEV, DPA, HU, 8>(p, st);
 }
 
 template <bool RBF, int DPA, int HU>
@@ -308,7 +331,7 @@ int launch_sigkern_warpfused(bool rbf, const float* A, const float* B, int rowsA
         return fail(GPSIG_E_BADARG, "sigkern_warpfused: bad sizes");
     WfParams p;
     p.A = A; p.B = B; p.rowsA = rowsA; p.rowsB = rowsB;
-    p.LP = wf_lanes_per_pair(ncols); p.log2LP = wf_log2(p.LP); p.G = 32 / p.LP; p.P = p.LP * kWfCols;
+    p.LP = wf_lanes_per_pair(rbf ? ncols + 1 : ncols); p.log2LP = wf_log2(p.LP); p.G = 32 / p.LP; p.P = p.LP * kWfCols;
     const int j_off = upper_only ? (i_off / p.G) * p.G : 0;  // first column group any of these rows keeps
     const int n2 = n2_total - j_off;
     p.njg = (n2 + p.G - 1) / p.G;

@@ -166,17 +166,21 @@ def test_kuf_fast_and_generic_paths_vs_oracle(kind, L, d, M, diff):
         assert_levels_close(got, ko.K_tens_vs_seq(Z, X, increments=inc, return_levels=True), msg="Kuf %s inc=%s" % (kind, inc))
 
 
+@pytest.mark.parametrize("path", ["GPSIG_WARPFUSED", "GPSIG_FUSED"])
 @pytest.mark.parametrize("kind", ["linear", "rbf"])
-def test_fused_kernel_is_bit_identical_to_the_pipeline(kind, monkeypatch):
-    """The opt-in fused Gram + recursion kernel (fused.cu, GPSIG_FUSED=1) against the default two-kernel path."""
+def test_fused_kernels_are_bit_identical_to_the_pipeline(kind, path, monkeypatch):
+    """The fused Gram + recursion kernels (warpfused.cu: default for Linear; fused.cu: opt-in) against the two-kernel
+    path (increment-Gram producer -> stream recursion): same arithmetic per entry, so the same bits."""
+    import ctypes
+    from gpsig_b200 import _lib
     X = random_walks(75, 64, 5, 31).reshape(75, -1)
     Y = random_walks(22, 64, 5, 32).reshape(22, -1)
     k, _ = _pair(kind, 64, 5, 4, lengthscales=1.4)
+    monkeypatch.setenv("GPSIG_WARPFUSED", "0")
     monkeypatch.delenv("GPSIG_FUSED", raising=False)
     ref_s, ref_r = k.K(X, return_levels=True).clone(), k.K(X, Y, return_levels=True).clone()
-    monkeypatch.setenv("GPSIG_FUSED", "1")
-    from gpsig_b200 import _lib
-    import ctypes
+    monkeypatch.setenv("GPSIG_WARPFUSED", "1" if path == "GPSIG_WARPFUSED" else "0")
+    monkeypatch.setenv("GPSIG_FUSED", "1" if path == "GPSIG_FUSED" else "0")
     lib = _lib.load()
     lib.gpsig_profile_reset(); lib.gpsig_profile_enable(1)
     got_s, got_r = k.K(X, return_levels=True), k.K(X, Y, return_levels=True)
