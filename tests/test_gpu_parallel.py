@@ -27,6 +27,9 @@ def test_sharded_world_size_1_matches_single():
     assert torch.equal(parallel.sharded_K_symm(k, X), k.K(X))
     k.normalization = False
     assert torch.equal(parallel.sharded_K_symm(k, X), k.K(X))
+    from gpsig_b200 import kernels
+    kl = kernels.SignatureLinear(64 * 4, 4, 4, lengthscales=1.3)
+    assert torch.equal(parallel.sharded_K_symm(kl, X), kl.K(X))
 
 
 def _free_port():
@@ -52,6 +55,9 @@ def _worker(rank, ws, port, q):
     K = parallel.sharded_K_symm(k, X)
     ref = k.K(X)
     ok = bool(torch.equal(K, ref))
+    from gpsig_b200 import kernels
+    kl = kernels.SignatureLinear(64 * 4, 4, 4, lengthscales=1.3)      # Linear takes the warp-fused kernel (row ranges per rank)
+    ok = ok and bool(torch.equal(parallel.sharded_K_symm(kl, X), kl.K(X)))
     # rectangular block, Kuf column shards and the data-parallel ELBO
     Y2 = random_walks(37, 64, 4, 12).reshape(37, -1)
     # the RBF path centres the points on the first sequence of each call (translation invariance), so row / column
