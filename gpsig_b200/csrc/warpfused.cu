@@ -17,6 +17,11 @@
 // buffered: strips cross the item boundary at different steps) and the y_j of its G pairs (each lane copies its
 // points from there when ITS strip starts the item).  Arithmetic per entry is the same as gram.cu + sigstream.cu, so the
 // results are bit-identical to the two-kernel path.
+//
+// Measured alternatives (round 1, K(X,X) N=4096 L=128 d=8 M=5): 4-column strips (half the state, 16 warps) 214 ms
+// Linear / 267 ms RBF -- the 32 distinct x rows per load and twice the shuffles per entry cost more than the extra warps
+// give; padding the x tile against the 2-way bank conflict of the row reads costs a warp of shared memory (165-171 ms);
+// fewer warps: 10 -> 188 ms, 8 -> 190 ms.  This version: 153 ms Linear (12 warps), 231 ms RBF (8 warps).
 #include <stdlib.h>
 
 #include <type_traits>
