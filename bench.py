@@ -16,9 +16,12 @@ problem size is fixed as N grows ("scaling": "strong").
             steps).
   e2e       the same through the public API with HOST buffers: X starts in pinned host memory, K ends in pinned
             host memory, both copies inside the timed region.
-  roofline  the dominant kernel (sigkern_fo_stream_kernel, the level recursion): algorithmic bytes per pair
-            (4 L1 L2 + 4 (M+1)) x pairs processed / its own CUDA-event duration (events recorded around
-            every launch inside the library: gpsig_profile_*), against MEASURED_PEAKS.json's hbm_gbs.
+  roofline  the dominant kernel of the step: algorithmic bytes per pair (4 L1 L2 + 4 (M+1)) x pairs processed
+            / its own CUDA-event duration (events recorded around every launch inside the library: gpsig_profile_*),
+            against MEASURED_PEAKS.json's hbm_gbs.  The default path is the warp-fused kernel (Gram + recursion in one
+            launch, no HBM intermediate: FP32-bound, the figure is the Gram bytes it stands for); `pipeline` carries the
+            same K steps through the HBM-staged two-kernel path (GPSIG_WARPFUSED=0) with the roofline of its recursion
+            kernel sigkern_fo_stream_kernel -- the kernel the HBM roofline really bounds.
   cpu_baseline  the fp64 NumPy oracle (op-for-op restatement of the reference, oracle/gpsig_oracle.py) on a bounded
             sample (n_s x n_s pairs of the same L/d/M) over all host cores; a reported baseline, not the target.
 
@@ -301,6 +304,26 @@ def run_ours(args, wl):
     # e2e: host buffers in, host buffer out
     step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)
+
+    # the same steps through the two-kernel pipeline (increment-Gram producer -> HBM -> stream recursion), the design the
+    # HBM roofline describes; the default path above is the warp-fused kernel, which never writes the Gram tensor
+    prof_pipe, ms_pipe = None, None
+    if prof["fused"][0] > 0:
+        os.environ["GPSIG_WARPFUSED"] = "0"
+        try:
+            step_dev()
+            lib.gpsig_profile_reset()
+            lib.gpsig_profile_enable(1)
+            ms_pipe, _ = timed(step_dev, args.steps)
+            lib.gpsig_profile_enable(0)
+            prof_pipe = {}
+            for name, c in (("prep", 0), ("producer", 1), ("recursion", 2), ("epilogue", 4)):
+                ms, n, un = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
+                _lib.check(lib.gpsig_profile_read(c, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(un)), "gpsig_profile_read")
+                prof_pipe[name] = (ms.value, n.value, un.value)
+            lib.gpsig_profile_reset()
+        finally:
+            os.environ.pop("GPSIG_WARPFUSED", None)
     if rank == 0:
         assert np.isfinite(Kh.numpy()[:8]).all()
 
@@ -313,22 +336,36 @@ def run_ours(args, wl):
     # roofline of the recursion kernel (rank 0's launches)
     peak, peak_src = load_peaks()
     b_pair = 4 * L * L + 4 * (M + 1)
-    r_ms, r_n, r_units = prof["recursion"]
-    kname, note = "sigkern_fo_stream_kernel", None
-    traffic = load_traffic("%s_recursion_bytes_per_launch" % args.workload) if world == 1 else None
-    if r_ms == 0 and prof["fused"][0] > 0:
-        # Linear takes the warp-fused kernel: Gram + recursion in one launch, the Gram tensor is never read from HBM.  The
-        # figure below is the ALGORITHMIC Gram bytes per second the kernel stands for (same formula), not DRAM traffic.
-        r_ms, r_n, r_units = prof["fused"]
-        kname, traffic = "sigkern_warpfused_kernel", None
-        note = "fused Gram + recursion: no HBM intermediate; achieved = algorithmic Gram bytes / kernel time (FP32-issue bound)"
-    achieved = (r_units * b_pair) / (r_ms * 1e-3) / 1e9 if r_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "bytes_per_pair": b_pair, "pairs_per_launch": r_units / max(r_n, 1), "launches": r_n,
-                "avg_launch_ms": r_ms / max(r_n, 1), "kernel_share_of_step": r_ms / ms_total}
-    if note:
-        roofline["note"] = note
+    def roof(kname, cls_prof, total_ms, traffic, note=None):
+        r_ms, r_n, r_units = cls_prof
+        achieved = (r_units * b_pair) / (r_ms * 1e-3) / 1e9 if r_ms > 0 else 0.0
+        out = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+               "traffic": traffic, "peak_source": peak_src, "bytes_per_pair": b_pair, "pairs_per_launch": r_units / max(r_n, 1),
+               "launches": r_n, "avg_launch_ms": r_ms / max(r_n, 1), "kernel_share_of_step": r_ms / total_ms}
+        if note:
+            out["note"] = note
+        return out
+
+    pipeline = None
+    if prof["fused"][0] > 0:
+        # default path: Gram + recursion in ONE kernel.  `achieved` is the ALGORITHMIC Gram bytes (same per-pair figure) the
+        # kernel stands for per second; its real DRAM traffic (`traffic`) is the inputs and outputs only -- the kernel is
+        # FP32-issue bound, the HBM roofline is what it removes.  The `pipeline` object below carries the HBM-staged
+        # two-kernel path measured in this same run.
+        roofline = roof("sigkern_warpfused_kernel", prof["fused"], ms_total,
+                        load_traffic("%s_warpfused_bytes_per_launch" % args.workload) if world == 1 else None,
+                        "fused Gram + recursion: no HBM intermediate (FP32-issue bound); see `pipeline.roofline` for the "
+                        "HBM-staged recursion kernel")
+        if prof_pipe is not None:
+            pipeline = {"ms_per_step": ms_pipe / args.steps, "value": N * N / (ms_pipe / args.steps * 1e-3), "unit": UNIT,
+                        "how": "same steps with GPSIG_WARPFUSED=0: increment-Gram producer -> HBM chunk -> stream recursion",
+                        "stages": {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
+                                   for k, v in prof_pipe.items()},
+                        "roofline": roof("sigkern_fo_stream_kernel", prof_pipe["recursion"], ms_pipe,
+                                         load_traffic("%s_recursion_bytes_per_launch" % args.workload) if world == 1 else None)}
+    else:
+        roofline = roof("sigkern_fo_stream_kernel", prof["recursion"], ms_total,
+                        load_traffic("%s_recursion_bytes_per_launch" % args.workload) if world == 1 else None)
     stages = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in prof.items()}
     p_ms, p_n, p_units = prof["producer"]
     if p_ms > 0:
@@ -359,6 +396,7 @@ def run_ours(args, wl):
         "gpu_launches": int(launches.item()),
         "clocks": clocks,
         "roofline": roofline,
+        "pipeline": pipeline,
         "stages": stages,
         "parity": parity,
         "cpu_baseline": cpu_baseline,

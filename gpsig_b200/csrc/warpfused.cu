@@ -21,7 +21,9 @@
 // Measured alternatives (round 1, K(X,X) N=4096 L=128 d=8 M=5): 4-column strips (half the state, 16 warps) 214 ms
 // Linear / 267 ms RBF -- the 32 distinct x rows per load and twice the shuffles per entry cost more than the extra warps
 // give; padding the x tile against the 2-way bank conflict of the row reads costs a warp of shared memory (165-171 ms);
-// fewer warps: 10 -> 188 ms, 8 -> 190 ms.  This version: 153 ms Linear (12 warps), 231 ms RBF (8 warps).
+// fewer warps: 10 -> 188 ms, 8 -> 190 ms.  Splitting the step loop into the LP "event" steps of an item period and
+// Lrow - LP test-free steps left Linear at 153 ms (12 warps, FMA-pipe / latency bound) but took RBF from 231 to 188 ms
+// (8 warps: the branches were what kept its two warps per scheduler from overlapping).
 #include <stdlib.h>
 
 #include <type_traits>
@@ -126,16 +128,21 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_warpfused_kernel(const W
     ty = tx;
     int s = -l;          // row of this lane's current item (negative: not started)
     int par = 0;         // x-tile buffer of this lane's current item
-    int s0 = 0, par0 = 0;  // row / buffer of strip 0's item (warp-uniform)
+    int par0 = 0;        // x-tile buffer of strip 0's item (warp-uniform)
 
-    auto step = [&](auto check_tag, long long T) {
+    // CHECK: lanes may be outside their stream (first LP - 1 and last LP - 1 steps of the warp).  EV: the step lies in the
+    // first LP steps of an item period, where things happen -- strip 0 stages the tiles (`stage`), every strip copies its
+    // column points and resets its state when it enters the item, the last strip writes the finished item.  The other
+    // Lrow - LP steps of a period run the same arithmetic without any of those tests.
+    auto step = [&](auto check_tag, auto ev_tag, long long T, bool stage) {
         constexpr bool CHECK = decltype(check_tag)::value;
+        constexpr bool EV = decltype(ev_tag)::value;
         // ---- strip 0 enters a new item: the warp stages x_i (other buffer) and the y_j of the G pairs ----
-        if (s0 == 0 && (!CHECK || T < total)) {
+        if (EV && stage) {
             const int i = tx.i, jg0 = wf_track_jg(p, tx) * p.G;
             wf_track_next(p, tx);
             const float4* srcx = reinterpret_cast<const float4*>(p.A + (long long)(p.i_off + i) * p.rowsA * DPA);
-            float4* dstx = reinterpret_cast<float4*>(xt + par0 * p.xfloats);
+            float4* dstx = reinterpret_cast<float4*>(xt + par0 * p.xfloats);  // par0 flips after the fill
             for (int e = lane; e < p.rowsA * (DPA / 4); e += 32) dstx[e] = __ldg(srcx + e);
             float4* dsty = reinterpret_cast<float4*>(yt);
             const int per = p.rowsB * (DPA / 4);
@@ -146,10 +153,11 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_warpfused_kernel(const W
                 for (int e = lane; e < per; e += 32) dsty[g * per + e] = __ldg(srcy + e);
             }
             __syncwarp();
+            par0 ^= 1;
         }
         const bool valid = CHECK ? (s >= 0 && T - l < total) : true;
         // ---- this strip enters the item: its column points move from the tile into registers ----
-        if (valid && s == 0) {
+        if (EV && valid && s == 0) {
 #pragma unroll
             for (int u = 0; u < NPT; ++u) {
                 const int t = t0 + u;
@@ -200,7 +208,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_warpfused_kernel(const W
             if (RBF) {
                 // lane l owns the increment columns 8 l - 1 .. 8 l + 6 (column -1 is a zero pad): the value to the LEFT of
                 // its first point belongs to lane l - 1, which evaluated this very row one step ago
-                if (s > 0) {
+                if (!EV || s > 0) {
                     d[0] = l == 0 ? 0.f : (f[0] - fl) - (fprev[0] - flprev);
 #pragma unroll
                     for (int u = 1; u < W; ++u) d[u] = (f[u] - f[u - 1]) - (fprev[u] - fprev[u - 1]);
@@ -232,7 +240,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_warpfused_kernel(const W
         if (valid) {
 #pragma unroll
             for (int m = 0; m < NLEV; ++m) ksum[m] += psum[m];
-            if (s == Lrow - 1 && l == LP - 1) {
+            if (EV && s == Lrow - 1 && l == LP - 1) {
                 const int j = wf_track_jg(p, ty) * p.G + q;
                 if (j < p.n2) {
                     float* o = p.out + (long long)(p.i_off + ty.i) * p.ldo + p.j_off + j;
@@ -243,15 +251,21 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_warpfused_kernel(const W
             }
         }
         // ---- advance the row counters (the lane's started at -l) ----
-        if (++s == Lrow) { s = 0; par ^= 1; wf_track_next(p, ty); }
-        if (++s0 == Lrow) { s0 = 0; par0 ^= 1; }
+        if (++s == Lrow) { s = 0; par ^= 1; wf_track_next(p, ty); }  // strip 0 wraps on the last step of a period
     };
 
-    long long T = 0;
-    const long long ramp = (LP - 1) < nsteps ? (LP - 1) : nsteps;
-    for (; T < ramp; ++T) step(std::true_type{}, T);
-    for (; T < total; ++T) step(std::false_type{}, T);
-    for (; T < nsteps; ++T) step(std::true_type{}, T);
+    const std::true_type yes{};
+    const std::false_type no{};
+    for (long long k = 0; k < nloc; ++k) {  // one period per item of strip 0
+        const long long base = k * Lrow;
+        if (k == 0) {
+            for (int e = 0; e < LP; ++e) step(yes, yes, base + e, e == 0);
+        } else {
+            for (int e = 0; e < LP; ++e) step(no, yes, base + e, e == 0);
+        }
+        for (long long T = base + LP; T < base + Lrow; ++T) step(no, no, T, false);
+    }
+    for (long long T = total; T < nsteps; ++T) step(yes, yes, T, false);  // the other strips finish the last item
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -269,16 +283,15 @@ int wf_lanes_per_pair(int ncols) {
     return 1 << wf_log2(need < 2 ? 2 : need);
 }
 
-// Default for LINEAR (measured 153 ms against 190-210 ms for producer + stream recursion on the headline shape).  RBF needs
-// ~230 registers, which leaves 8 warps per SM: 231 ms against 202-226 ms for the two-kernel path, so RBF only takes this
-// path on request (GPSIG_WARPFUSED=1).  GPSIG_WARPFUSED=0 disables it altogether.
+// Default path of K(X, X) / K(X, X2) for the shapes it is instantiated for (measured on the headline shape: Linear 153 ms,
+// RBF 188 ms per step against 190-210 / 202-217 ms for producer + stream recursion).  GPSIG_WARPFUSED=0 switches back to
+// the two-kernel pipeline (bench.py does that for its "pipeline" pass).
 bool warpfused_supported(bool rbf, int d, int nlev, int ncols, int rowsA) {
+    (void)rbf;
     if (nlev < 2 || nlev > 5 || d > 8) return false;
     if (ncols + 1 > 32 * kWfCols || rowsA < 48) return false;
     const char* v = getenv("GPSIG_WARPFUSED");
-    if (v && *v == '0') return false;
-    if (rbf) return v && *v == '1';
-    return true;
+    return !(v && *v == '0');
 }
 
 template <bool RBF, int NLEV, int DPA, int HU, int MAXW>
