@@ -106,3 +106,27 @@ def test_product_never_imports_the_oracle():
     for path in glob.glob(os.path.join(ROOT, "gpsig_b200", "*.py")):
         src = open(path).read()
         assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S).replace("# oracle", ""), path
+
+
+def test_low_rank_projection_csc_matches_the_dense_definition():
+    """Host logic of the low-rank mode (no device): the CSC form handed to gpsig_lr_hadamard_csc encodes exactly
+    C = scale * (A (x) B) R with row q of R pairing A[q % k1] and B[q // k1] (low_rank_calculations.py:165-170, :182-193)."""
+    from gpsig_b200 import low_rank_calculations as L
+    from oracle import gpsig_oracle as O
+    rng = np.random.default_rng(0)
+    k1, k2, r = 5, 7, 6
+    proj = L.draw_projection(k1, k2, r, "sqrt", seed=[3, 1], device="cpu")
+    again = L.draw_projection(k1, k2, r, "sqrt", seed=[3, 1], device="cpu")
+    assert np.array_equal(proj.dense, again.dense)                       # same seed, same projection
+    colptr, ia, ib, val = (t.numpy() for t in (proj.colptr, proj.ia, proj.ib, proj.val))
+    assert colptr[0] == 0 and colptr[-1] == len(val) == np.count_nonzero(proj.dense)
+    A, B = rng.standard_normal((4, k1)), rng.standard_normal((4, k2))
+    C = np.zeros((4, r))
+    for c in range(r):
+        for e in range(colptr[c], colptr[c + 1]):
+            C[:, c] += A[:, ia[e]] * B[:, ib[e]] * val[e]
+    C *= proj.scale
+    ref = O.lr_hadamard_prod_sparse(A, B, proj.dense, O.sparse_scale(k1 * k2, "sqrt"))
+    np.testing.assert_allclose(C, ref, rtol=1e-6, atol=1e-7)
+    sub = L.draw_projection(k1, k2, r, "lin", seed=5, device="cpu")       # subsampling: one signed entry per column
+    assert np.array_equal(sub.colptr.numpy(), np.arange(r + 1)) and set(np.abs(sub.val.numpy())) == {1.0}
