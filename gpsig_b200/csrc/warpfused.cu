@@ -317,14 +317,11 @@ static int launch_wf_maxw(WfParams& p, cudaStream_t st) {
 }
 
 // register budget per thread: 12 warps -> 168, 8 warps -> 255 (allocation granule: 4 warps).  LINEAR fits 168; RBF needs
-// ~230 (8 more points' worth of exponent arguments and the previous row's values), so it runs 8 warps unless
-// GPSIG_WARPFUSED_RBF12=1 asks for the spilling 12-warp build (experiment knob)
+// ~230 (the exponent arguments of 8 points and the previous row's values), so it runs 8 warps per SM (a 12-warp build
+// spills ~400 bytes per thread and was measured at 445 ms against 231 ms)
 template <bool RBF, int NLEV, int DPA, int HU>
 static int launch_wf_inst(WfParams& p, cudaStream_t st) {
-    if (!RBF) return launch_wf_maxw<RBF, NLEV, DPA, HU, 12>(p, st);
-    const char* v = getenv("GPSIG_WARPFUSED_RBF12");
-    if (v && *v == '1') return launch_wf_maxw<RBF, NLEV, DPA, HU, RBF ? 12 : 8>(p, st);
-    return launch_wf_maxw<RBF, NLEV, DPA, HU, 8>(p, st);
+    return launch_wf_maxw<RBF, NLEV, DPA, HU, RBF ? 8 : 12>(p, st);
 }
 
 template <bool RBF, int DPA, int HU>
