@@ -7,10 +7,10 @@ bench.py -- sequence-pairs/sec of the full signature-kernel covariance K(X, X) (
         bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference ...      # the reference's own algorithm (fp64 NumPy oracle) on the host cores
 
-A "step" is one evaluation of K(X, X) for the whole workload: point prep -> chunked increment-Gram producer ->
-bulk-copy-staged level recursion -> normalise / weight / sum -> mirror (gpsig_b200.kernels.SignatureKernel.K; with N > 1
-gpsig_b200.parallel.sharded_K_symm: row blocks dealt over the ranks, ONE all-gather of the assembled rows).  The
-problem size is fixed as N grows ("scaling": "strong").
+A "step" is one evaluation of K(X, X) for the whole workload: point prep -> warp-fused increment-Gram + level recursion
+kernel (or, as the `pipeline` pass: chunked increment-Gram producer -> bulk-copy-staged stream recursion) -> normalise /
+weight / sum -> mirror (gpsig_b200.kernels.SignatureKernel.K; with N > 1 gpsig_b200.parallel.sharded_K_symm: row blocks
+dealt over the ranks, ONE all-gather of the assembled rows).  The problem size is fixed as N grows ("scaling": "strong").
 
   value     N^2 output pairs / step time, X already resident in HBM (CUDA events, max over ranks, L2 flushed between
             steps).
@@ -389,7 +389,7 @@ def run_ours(args, wl):
         "config": {"workload": wl["desc"], "static_kernel": kind, "N": N, "L": L, "d": d, "M": M, "order": 1,
                    "normalization": True, "symmetric_half_computed": True,
                    "parallelism": "row-sharded x%d + one all-gather" % world if world > 1 else "single GPU",
-                   "l2": "flushed between steps (512 MiB memset); the increment-Gram chunk buffer is larger than L2",
+                   "l2": "flushed between steps (512 MiB memset)",
                    "workspace_budget_GiB": settings.workspace_budget_bytes / (1 << 30)},
         "e2e": {"value": N * N / (ms_e2e / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(Xh.numel() * 4),
                 "d2h_bytes_per_step": int(Kh.numel() * 4), "ms_per_step": ms_e2e / args.steps},
