@@ -180,9 +180,51 @@ def gen_lowrank():
     return len(out)
 
 
+def walks(n, L, d, seed):
+    rng = np.random.default_rng(seed)
+    return (np.cumsum(rng.standard_normal((n, L, d)), axis=1) / np.sqrt(L)).reshape(n, L * d)
+
+
+def gen_configs():
+    """BASELINE.json's configurations at sizes the reference (on the NumPy stand-in) finishes in seconds: configs[0] in
+    full (SignatureRBF K(X,X) N=32 L=20 d=3 M=3, plus the notebook's order=M linear case), and the tile shapes of
+    configs[1] (L=64 d=6 M=4), configs[2-3] (L=128 d=8 M=5; Kuf with incremental inducing tensors) on a few sequences."""
+    out = {}
+
+    def put(tag, cls, L, d, M, n, seed, nz=0, **kw):
+        k = getattr(kr, cls)(L * d, d, M, **kw)
+        X = walks(n, L, d, seed)
+        out[tag + ".X"] = X
+        out[tag + ".K"] = npy(k.K(T(X)))
+        out[tag + ".K_lv"] = npy(k.K(T(X), return_levels=True))
+        X2 = walks(max(2, n // 3), L, d, seed + 1)
+        out[tag + ".X2"] = X2
+        out[tag + ".K_rect"] = npy(k.K(T(X), T(X2)))
+        if nz:
+            Z = 0.4 * np.random.default_rng(seed + 2).standard_normal((M * (M + 1) // 2, nz, 2, d))
+            out[tag + ".Z"] = Z
+            r = npy(k.K_tens_n_seq_covs(T(Z), T(X), full_X_cov=False, increments=True))
+            out[tag + ".Kzz"], out[tag + ".Kzx"], out[tag + ".Kxx"] = r
+
+    ls3 = [0.9, 1.1, 1.4]
+    put("cfg1_rbf", "SignatureRBF", 20, 3, 3, 32, 0, lengthscales=ls3)
+    put("cfg1_rbf_nonorm", "SignatureRBF", 20, 3, 3, 32, 0, lengthscales=ls3, normalization=False)
+    put("cfg1_lin_orderM", "SignatureLinear", 20, 3, 3, 32, 0, order=3, normalization=False, lengthscales=None)
+    put("cfg2_lin_tile", "SignatureLinear", 64, 6, 4, 12, 1, lengthscales=1.0)
+    put("cfg4_rbf_tile", "SignatureRBF", 128, 8, 5, 6, 2, nz=8, lengthscales=float(np.sqrt(8.0)))
+    put("cfg4_lin_tile", "SignatureLinear", 128, 8, 5, 6, 2, nz=8, lengthscales=1.0)
+    np.savez_compressed(os.path.join(HERE, "configs.npz"), **out)
+    return len(out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "configs":
+        print("configs:", gen_configs(), "arrays")
+        print("configs.npz", os.path.getsize(os.path.join(HERE, "configs.npz")), "bytes")
+        sys.exit(0)
     print("algs:", gen_algs(), "arrays")
     print("kernels:", gen_kernels(), "arrays")
     print("lowrank:", gen_lowrank(), "arrays")
-    for f in ("algs.npz", "kernels.npz", "lowrank.npz"):
+    print("configs:", gen_configs(), "arrays")
+    for f in ("algs.npz", "kernels.npz", "lowrank.npz", "configs.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
