@@ -740,3 +740,42 @@ def brute_force_first_order(Delta, num_levels):
                 tot += p
         K.append(tot)
     return np.array(K)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Groundwork for the backward pass (the reference gets it from TF autodiff through
+# signature_algs.py:26-33).  Reverse-mode of the first-order recursion, pinned by finite differences in
+# tests/test_oracle_props.py -- the checker the device backward kernels will be held to.
+# ----------------------------------------------------------------------------------------------------------------
+def _excl_suffix_sum(a, axis):
+    """transpose of the exclusive cumsum: out[k] = sum_{k' > k} a[k']."""
+    r = np.flip(np.cumsum(np.flip(a, axis=axis), axis=axis), axis=axis)
+    return r - a
+
+
+def signature_kern_first_order_vjp(Delta, num_levels, G):
+    """
+    Vector-Jacobian product of K = signature_kern_first_order(Delta, num_levels, difference=False)
+    (signature_algs.py:28-33).  Delta (n1, r, n2, c); G = dL/dK with K's shape (num_levels+1, n1, n2).
+    Returns dL/dDelta (n1, r, n2, c).
+
+    Forward: R_1 = Delta, R_{m+1} = Delta * E(R_m) with E the exclusive 2-D prefix sum, K_m = sum R_m.
+    Reverse: B_M = G_M, B_m = G_m + E^T(Delta * B_{m+1}) with E^T the exclusive 2-D SUFFIX sum;
+             dL/dDelta = B_1 + sum_{m >= 2} B_m * E(R_{m-1}).
+    """
+    Delta = np.asarray(Delta, dtype=np.float64)
+    G = np.asarray(G, dtype=np.float64)
+    E = lambda R: _excl_cumsum(_excl_cumsum(R, 1), 3)              # noqa: E731
+    Et = lambda R: _excl_suffix_sum(_excl_suffix_sum(R, 1), 3)     # noqa: E731
+    ER = [None, None]                                               # ER[m] = E(R_{m-1}) for m >= 2
+    R = Delta
+    for m in range(2, num_levels + 1):
+        ER.append(E(R))
+        R = Delta * ER[m]
+    B = G[num_levels][:, None, :, None] * np.ones_like(Delta)
+    grad = np.zeros_like(Delta)
+    for m in range(num_levels, 0, -1):
+        grad += B if m == 1 else B * ER[m]
+        if m > 1:
+            B = G[m - 1][:, None, :, None] + Et(Delta * B)
+    return grad

@@ -101,3 +101,23 @@ def test_base_conditional_and_gauss_kl_against_dense_gaussian_algebra():
     want = sum(0.5 * (np.trace(q_sqrt[r] @ q_sqrt[r].T) + q_mu[:, r] @ q_mu[:, r] - Zn
                       - np.linalg.slogdet(q_sqrt[r] @ q_sqrt[r].T)[1]) for r in range(R))
     np.testing.assert_allclose(O.gauss_kl(q_mu, q_sqrt), want, rtol=1e-9)
+
+
+def test_first_order_vjp_matches_finite_differences():
+    """groundwork for the backward pass: reverse-mode recursion (suffix sums) against central differences."""
+    rng = np.random.default_rng(17)
+    n1, r, n2, c, M = 2, 5, 3, 4, 4
+    Delta = 0.3 * rng.standard_normal((n1, r, n2, c))
+    G = rng.standard_normal((M + 1, n1, n2))
+    loss = lambda D: float(np.sum(G * O.signature_kern_first_order(D, M, difference=False)))  # noqa: E731
+    grad = O.signature_kern_first_order_vjp(Delta, M, G)
+    num = np.zeros_like(Delta)
+    h = 1e-6
+    it = np.nditer(Delta, flags=["multi_index"])
+    for _ in it:
+        idx = it.multi_index
+        Dp, Dm = Delta.copy(), Delta.copy()
+        Dp[idx] += h
+        Dm[idx] -= h
+        num[idx] = (loss(Dp) - loss(Dm)) / (2 * h)
+    np.testing.assert_allclose(grad, num, rtol=1e-6, atol=1e-8)
