@@ -35,7 +35,15 @@ _PROTOTYPES = {
                                              ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, ctypes.c_int, ctypes.c_int,
                                              ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, ctypes.c_long, ctypes.c_long,
                                              ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "gpsig_seq_kern_levels_blocks": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, _c_float_p, ctypes.c_int, ctypes.c_int,
+                                                    _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p,
+                                                    ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
+                                                    ctypes.c_int, _c_float_p, ctypes.c_long, ctypes.c_void_p,
+                                                    ctypes.c_size_t, ctypes.c_void_p]),
+    "gpsig_seq_kern_diag_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_size_t]),
+    "gpsig_set_knob": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
     "gpsig_mirror_upper": (ctypes.c_int, [_c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "gpsig_assemble_symmetric": (ctypes.c_int, [_c_float_p, ctypes.c_void_p, ctypes.c_int, _c_float_p, ctypes.c_void_p]),
     "gpsig_seq_kern_diag_levels": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, _c_float_p, ctypes.c_int, ctypes.c_int,
                                                   ctypes.c_int, _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p,
                                                   ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
@@ -58,6 +66,7 @@ _PROTOTYPES = {
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
+ABI_VERSION = 200  # include/gpsig_b200.h GPSIG_B200_VERSION
 
 _lib = None
 
@@ -75,16 +84,29 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    # build() is digest-cached (stamp file over sources + header + flags): a stale library is rebuilt, a current one costs
+    # one hash of the sources.  Without nvcc (a box that only received the prebuilt .so) the existing library is used.
     path = _build.LIBPATH
-    if not os.path.exists(path) or os.environ.get("GPSIG_B200_REBUILD"):
-        path = _build.build()
+    try:
+        path = _build.build(force=bool(os.environ.get("GPSIG_B200_REBUILD")))
+    except Exception:
+        if not os.path.exists(path):
+            raise
     lib = ctypes.CDLL(path)
     for name, (res, args) in _PROTOTYPES.items():
         fn = getattr(lib, name)  # AttributeError here = header / library mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
+    if lib.gpsig_version() != ABI_VERSION:
+        raise GPSigError("libgpsig_b200.so reports ABI version %d, the Python host expects %d: rebuild (GPSIG_B200_REBUILD=1)"
+                         % (lib.gpsig_version(), ABI_VERSION))
     _lib = lib
     return lib
+
+
+def set_knob(name, value):
+    """gpsig_set_knob: runtime switch of a tuning knob (bench.py's `pipeline` pass, experiments)."""
+    check(load().gpsig_set_knob(name.encode(), int(value)), "gpsig_set_knob")
 
 
 def check(rc, what):

@@ -5,7 +5,9 @@
 #include <mutex>
 #include <vector>
 
-#include "common.cuh"
+#include <stdlib.h>
+
+#include "internal.cuh"
 
 namespace gpsig {
 
@@ -62,6 +64,19 @@ int num_sms() {
     }
     return cached;
 }
+
+// ---- tuning knobs: environment read once, then only gpsig_set_knob() changes them ---------------------------------
+static int env_int_once(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+static EnvKnobs& knobs_mut() {
+    static EnvKnobs k = {env_int_once("GPSIG_WARPFUSED", 1), env_int_once("GPSIG_WARPFUSED_WARPS", 0),
+                         env_int_once("GPSIG_STREAM_NCW", 0), env_int_once("GPSIG_STREAM_R", 0),
+                         env_int_once("GPSIG_STREAM_S", 0), env_int_once("GPSIG_TENS_TC", 1)};
+    return k;
+}
+const EnvKnobs& env_knobs() { return knobs_mut(); }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -135,6 +150,19 @@ extern "C" int gpsig_profile_read(int cls, double* total_ms, long long* launches
     if (total_ms) *total_ms = ms;
     if (launches) *launches = n;
     if (units) *units = un;
+    return GPSIG_OK;
+}
+
+extern "C" int gpsig_set_knob(const char* name, int value) {
+    if (!name) return gpsig::fail(GPSIG_E_BADARG, "set_knob: null name");
+    gpsig::EnvKnobs& k = gpsig::knobs_mut();
+    if (!strcmp(name, "warpfused")) k.warpfused = value;
+    else if (!strcmp(name, "warpfused_warps")) k.warpfused_warps = value;
+    else if (!strcmp(name, "stream_ncw")) k.stream_ncw = value;
+    else if (!strcmp(name, "stream_r")) k.stream_r = value;
+    else if (!strcmp(name, "stream_s")) k.stream_s = value;
+    else if (!strcmp(name, "tens_tc")) k.tens_tc = value;
+    else return gpsig::fail(GPSIG_E_BADARG, "set_knob: unknown knob '%s'", name);
     return GPSIG_OK;
 }
 

@@ -43,39 +43,29 @@ __device__ __forceinline__ float kern_eval(float dot, float sq, float xx, float 
 }
 
 // ---- prep: out[n, r, 0..DP) = scaled points (mode 0) or scaled time increments (mode 1), zero padded to DP --------
-//      mode 2 (RBF fast path): xh = (x - centre) / lengthscale * sqrt(log2 e), then (xh, -|xh|^2/2, 1, 0...) so that
-//      log2 k(x, y) = <xh, yh> - |xh|^2/2 - |yh|^2/2 is ONE dot product of the augmented vectors (the reader swaps the
-//      two extra components on the y side).  `centre` (d floats, may be NULL) only improves conditioning: the RBF
-//      kernel is translation invariant (kernels.py:765-776, :862-864).
+//      mode 3 (RBF fast paths): points times sqrt(log2(e) / 2) / lengthscale, so that log2 k(x, y) = -|x' - y'|^2
+//      (kernels.py:765-776, :862-864): the readers evaluate the squared distance from DIFFERENCES of nearby points
+//      (warpfused.cu, tens.cu) or directly (the chunk producer below) -- never through |x|^2 + |y|^2 - 2<x, y>.
 __global__ void prep_points_kernel(const float* __restrict__ X, long long n, int L, int d, const float* __restrict__ inv_ls,
-                                   int mode, int DP, float* __restrict__ out, float* __restrict__ norms,
-                                   const float* __restrict__ centre) {
+                                   int mode, int DP, float* __restrict__ out, float* __restrict__ norms) {
     const int increments = mode == 1;
     const int Lo = increments ? L - 1 : L;
     const long long total = n * (long long)Lo;
-    const float rs = mode == 2 ? 1.2011224087864498f : 1.f;  // sqrt(log2 e)
-    const int nd = mode == 2 ? DP - 4 : DP;                  // feature slots
+    const float rs = mode == 3 ? 0.8493218002880191f : 1.f;  // sqrt(log2(e) / 2)
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const long long seq = idx / Lo;
         const int r = (int)(idx - seq * Lo);
         const float* x0 = X + (seq * L + r) * d;
         float nn = 0.f;
-        for (int c = 0; c < nd; ++c) {
+        for (int c = 0; c < DP; ++c) {
             float v = 0.f;
             if (c < d) {
                 const float s = (inv_ls ? inv_ls[c] : 1.f) * rs;
-                const float x = (mode == 2 && centre) ? x0[c] - centre[c] : x0[c];
-                v = increments ? (x0[d + c] - x0[c]) * s : x * s;
+                v = increments ? (x0[d + c] - x0[c]) * s : x0[c] * s;
             }
             out[idx * DP + c] = v;
             nn = fmaf(v, v, nn);
-        }
-        if (mode == 2) {
-            out[idx * DP + nd] = -0.5f * nn;
-            out[idx * DP + nd + 1] = 1.f;
-            out[idx * DP + nd + 2] = 0.f;
-            out[idx * DP + nd + 3] = 0.f;
         }
         if (norms) norms[idx] = nn;
     }
@@ -191,9 +181,10 @@ __global__ void __launch_bounds__(256) delta_producer_kernel(const ProdParams p)
 
 // ---- fast producer for the two headline static kernels -------------------------------------------------------------
 // LINEAR (RBF = false): A / B are time increments, out = <dx_s, dy_t>.          DPA = padded d.
-// RBF    (RBF = true) : A / B are augmented points (prep mode 2), f = 2^<x', y'>, out = 2-D increment of f.
-// Same thread mapping, skip logic and output addressing as delta_producer_kernel; the dot products run on packed
-// fma.rn.f32x2 (two features per instruction, sm_100), the exponential is one ex2.approx.
+// RBF    (RBF = true) : A / B are scaled points (prep mode 3), f = 2^(-|x' - y'|^2) from the differences directly
+//                       (robust wherever the data sits), out = 2-D increment of f.
+// Same thread mapping, skip logic and output addressing as delta_producer_kernel; the arithmetic runs on packed
+// add / fma.rn.f32x2 (two features per instruction, sm_100), the exponential is one ex2.approx.
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -203,7 +194,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 template <bool RBF, int DPA>
 __global__ void __launch_bounds__(256) delta_producer_fast_kernel(const ProdParams p) {
     extern __shared__ __align__(16) float sA[];  // [rowsA][DPA] of the current row sequence
-    constexpr int H = RBF ? DPA / 2 - 1 : DPA / 2;  // float2 pairs that carry data (the last RBF pair is padding)
+    constexpr int H = DPA / 2;
     constexpr int NPT = RBF ? 5 : 4;
     const int tpp = p.P >> 2;      // threads per pair row
     const int ppb = blockDim.x / tpp;
@@ -227,9 +218,9 @@ __global__ void __launch_bounds__(256) delta_producer_fast_kernel(const ProdPara
         const float2* src = reinterpret_cast<const float2*>(p.B + ((long long)j * p.rowsB + tc) * DPA);
 #pragma unroll
         for (int h = 0; h < H; ++h) y[u][h] = ok ? src[h] : make_float2(0.f, 0.f);
-        if (RBF) {  // y side of the augmented product: (..., 1, -|y|^2/2)
-            const float2 a = y[u][H - 1];
-            y[u][H - 1] = make_float2(a.y, a.x);
+        if (RBF) {  // the evaluation adds x to the NEGATED point
+#pragma unroll
+            for (int h = 0; h < H; ++h) y[u][h] = make_float2(-y[u][h].x, -y[u][h].y);
         }
     }
     const int group_last_j = (j / p.G) * p.G + p.G - 1;
@@ -267,9 +258,16 @@ __global__ void __launch_bounds__(256) delta_producer_fast_kernel(const ProdPara
             for (int u = 0; u < 4; ++u) {
                 float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int h = 0; h < H; ++h) acc = __ffma2_rn(x[h], y[u][h], acc);
+                for (int h = 0; h < H; ++h) {
+                    if (RBF) {
+                        const float2 df = __fadd2_rn(x[h], y[u][h]);
+                        acc = __ffma2_rn(df, df, acc);
+                    } else {
+                        acc = __ffma2_rn(x[h], y[u][h], acc);
+                    }
+                }
                 const float v = acc.x + acc.y;
-                f[u] = RBF ? ex2_approx(v) : v;
+                f[u] = RBF ? ex2_approx(-v) : v;
             }
             if (RBF) {
                 const float nb = __shfl_down_sync(0xffffffffu, f[0], 1);
@@ -277,8 +275,11 @@ __global__ void __launch_bounds__(256) delta_producer_fast_kernel(const ProdPara
                 if (any5) {  // uniform branch
                     float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int h = 0; h < H; ++h) acc = __ffma2_rn(x[h], y[NPT - 1][h], acc);
-                    const float v = ex2_approx(acc.x + acc.y);
+                    for (int h = 0; h < H; ++h) {
+                        const float2 df = __fadd2_rn(x[h], y[NPT - 1][h]);
+                        acc = __ffma2_rn(df, df, acc);
+                    }
+                    const float v = ex2_approx(-(acc.x + acc.y));
                     if (direct5) f[NPT - 1] = v;
                 }
             }
@@ -332,10 +333,10 @@ int launch_delta_producer_fast(bool rbf, const ProdParams& p, int DPA, cudaStrea
     ProfScope prof(GPSIG_PROF_PRODUCER, st, p.diag ? (double)p.nj : (double)p.ni * p.nj);
     if (rbf) {
         switch (DPA) {
+            case 4: return launch_producer_fast_dpa<true, 4>(p, st);
             case 8: return launch_producer_fast_dpa<true, 8>(p, st);
             case 12: return launch_producer_fast_dpa<true, 12>(p, st);
             case 16: return launch_producer_fast_dpa<true, 16>(p, st);
-            case 20: return launch_producer_fast_dpa<true, 20>(p, st);
         }
     } else {
         switch (DPA) {
@@ -403,13 +404,13 @@ int launch_delta_producer(int kind, const ProdParams& p, int DP, bool diff2d, cu
 }
 
 int launch_prep_points(const float* X, long long n, int L, int d, const float* inv_ls, int mode, int DP, float* out,
-                       float* norms, cudaStream_t st, const float* centre) {
+                       float* norms, cudaStream_t st) {
     const long long total = n * (long long)(mode == 1 ? L - 1 : L);
     if (total <= 0) return GPSIG_OK;
     ProfScope prof(GPSIG_PROF_PREP, st, (double)n);
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)num_sms() * 16;
-    prep_points_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(X, n, L, d, inv_ls, mode, DP, out, norms, centre);
+    prep_points_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(X, n, L, d, inv_ls, mode, DP, out, norms);
     return check_launch();
 }
 

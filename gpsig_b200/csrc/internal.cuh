@@ -4,6 +4,15 @@
 
 namespace gpsig {
 
+// tuning / experiment knobs from the environment, read ONCE (first use) -- see tools/README.md
+struct EnvKnobs {
+    int warpfused;        // GPSIG_WARPFUSED (default 1): 0 = two-kernel pipeline instead of the warp-fused kernel
+    int warpfused_warps;  // GPSIG_WARPFUSED_WARPS (default 0 = as many as fit)
+    int stream_ncw, stream_r, stream_s;  // GPSIG_STREAM_NCW / _R / _S (0 = default geometry)
+    int tens_tc;          // GPSIG_TENS_TC (default 1): 0 = CUDA-core Kuf kernel even where the tcgen05 one applies
+};
+const EnvKnobs& env_knobs();
+
 constexpr int kSpecMaxQ = 8, kSpecMaxD = 16;
 struct KernParams {
     float a, b;  // poly: gamma, degree; mix: mixing
@@ -103,9 +112,9 @@ struct ProdParams {
 int launch_delta_producer(int kind, const ProdParams& p, int DP, bool diff2d, cudaStream_t st);
 // fast producers (LINEAR on increments, RBF on augmented points); DPA = floats per prepared point
 int launch_delta_producer_fast(bool rbf, const ProdParams& p, int DPA, cudaStream_t st);
-// mode 0: scaled points, 1: scaled time increments, 2: RBF-augmented centred points (DP includes the 4 extra slots)
+// mode 0: scaled points, 1: scaled time increments, 3: points scaled so that log2 k_rbf(x, y) = -|x' - y'|^2
 int launch_prep_points(const float* X, long long n, int L, int d, const float* inv_ls, int mode, int DP, float* out,
-                       float* norms, cudaStream_t st, const float* centre = nullptr);
+                       float* norms, cudaStream_t st);
 KernParams make_kern_params(int kind, const float* params);
 
 int fo_lanes_per_pair(int ncols);
@@ -119,15 +128,17 @@ int launch_sigkern_stream(const float* buf, const StreamGeom& g, long long nitem
                           int upper_only, int i_off, int j_off, long long ldo, long long lvl_stride, float* out,
                           cudaStream_t st);
 // Warp-autonomous fused Gram + recursion (warpfused.cu): every warp computes and consumes its own increment rows.
+constexpr int kWfMaxRowBlocks = 32;
+// RBF strips whose points lie further than this (squared, in the scaled units of prep mode 3: log2 k = -|x - y|^2) from
+// the strip's anchor switch the call to the direct-difference instantiation (fp32 error of the anchored form is about
+// 1.5e-7 |u|^2 relative to k)
+constexpr float kWfJumpThreshold = 4.0f;
 bool warpfused_supported(bool rbf, int d, int nlev, int ncols, int rowsA);
-int launch_sigkern_warpfused(bool rbf, const float* A, const float* B, int rowsA, int rowsB, int DPA, int ncols, int n1,
-                             int n2_total, int nlev, int upper_only, int i_off, long long ldo, long long lvl_stride, float* out,
+int launch_wf_jump_flag(const float* B, long long n, int rows, int D, unsigned* flag, bool reset, cudaStream_t st);
+int launch_sigkern_warpfused(bool rbf, const float* A, const float* B, const unsigned* flag, int rowsA, int rowsB, int D,
+                             int npts, int n2, int nlev, int upper_only, int diag, int nblk, const int* blk_begin,
+                             const int* blk_end, const long long* blk_out_row, long long ldo, long long lvl_stride, float* out,
                              cudaStream_t st);
-// Fused Gram + recursion (fused.cu): level stacks straight from prepared points, no chunk buffer.
-bool fused_supported(bool rbf, int d, int nlev, int LP, int rowsA);
-int launch_sigkern_fused(bool rbf, const float* A, const float* B, int rowsA, int rowsB, int d, int DPA, int P, int LP,
-                         long long nitems, int n1, int n2, int nlev, int upper_only, int i_off, int j_off, long long ldo,
-                         long long lvl_stride, float* out, cudaStream_t st);
 // Higher-order recursion (signature_algs.py:37-74), same addressing.
 int launch_sigkern_ho(const float* M, int n1, int Lrows, int n2, int ncols, long long si, long long ss, long long sj,
                       int nlev, int order, int difference, int upper_only, int i_off, int j_off, long long ldo,

@@ -95,21 +95,17 @@ static int ilog2_exact(int x) {
     return l;
 }
 
-static int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
-}
-
 // geometry of a launch over `nitems` items of `rows` increment rows each
 StreamGeom stream_geometry(long long nitems, int rows, int LP, int nlev) {
     StreamGeom g;
     // consumer warps per CTA / rows per bulk copy / ring depth (GPSIG_STREAM_* are tuning knobs for experiments)
     const int maxw = nlev <= 5 ? 12 : 8;
-    g.ncw = nlev <= 5 ? env_int("GPSIG_STREAM_NCW", 11) : 7;
+    const EnvKnobs& ek = env_knobs();
+    g.ncw = nlev <= 5 ? (ek.stream_ncw > 0 ? ek.stream_ncw : 11) : 7;
     if (g.ncw > maxw - 1) g.ncw = maxw - 1;
     if (g.ncw < 1) g.ncw = 1;
-    g.R = env_int("GPSIG_STREAM_R", 4);
-    g.S = env_int("GPSIG_STREAM_S", nlev <= 5 ? 2 : 3);
+    g.R = ek.stream_r > 0 ? ek.stream_r : 4;
+    g.S = ek.stream_s > 0 ? ek.stream_s : (nlev <= 5 ? 2 : 3);
     if (g.R < 1) g.R = 1;
     if (g.S < 2) g.S = 2;
     while ((size_t)g.ncw * g.S * ((size_t)g.R * 2048 + 16) > 232448 && g.S > 2) --g.S;

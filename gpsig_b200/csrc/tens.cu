@@ -210,11 +210,17 @@ static int launch_tsf(const TsfParams& p, cudaStream_t st) {
 
 // ---- fast fused tensor-vs-sequence kernel (first order, LINEAR / RBF) ----------------------------------------------
 // kernels.py:313-340 + signature_algs.py:101-127 without the (T, nz, n, L) Gram: one thread sweeps time for TWO
-// sequences against ONE inducing tensor whose T (x2) component points sit in shared memory (broadcast reads); the T
+// sequences against ONE inducing tensor whose T component points sit in shared memory (broadcast reads); the T
 // running prefixes of both sequences live in registers (everything is unrolled over the component index).
 //   LINEAR: h_k(t) = <dz_k, dx_t>        (dz = z^1 - z^0 with increments, dx = time increment: bilinearity of :330, :114)
-//   RBF   : v_k(t) = 2^<z'^1, x'> - 2^<z'^0, x'>  on the augmented points of prep mode 2;  h_k(t) = v_k(t) - v_k(t-1)
-// The dot products run on packed fma.rn.f32x2.
+//   RBF   : points scaled so that log2 k = -|z - x|^2 (prep mode 3).  With w = x_t - z^0_k,
+//             k(z^0_k, x_t) = 2^(-|w|^2)                                        (direct differences)
+//             k(z^1_k, x_t) = 2^(-|w|^2 + 2 <w, dz_k> - |dz_k|^2),  dz_k = z^1_k - z^0_k   (anchored on z^0_k)
+//           so every term is bounded by the distance of x_t to the tensor point and by the tensor's own increment -- no
+//           global centre (round 1 expanded around X[0, 0, :]).  A tensor whose increment is long (|dz|^2 above
+//           kWfJumpThreshold in scaled units) takes the direct form for z^1 too; the test is uniform over the warp.
+//           v_k(t) = k(z^1) - k(z^0) (or k(z^0) without increments);  h_k(t) = v_k(t) - v_k(t-1).
+// The arithmetic runs on packed add / fma.rn.f32x2.
 __device__ __forceinline__ float tsf_ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -230,29 +236,49 @@ struct TsfFastParams {
     float* out;       // (NLEV + 1, nz, n)
 };
 
-constexpr int kTsfZPerBlock = 4;   // warps per block, one inducing tensor each (3 blocks / SM at ~160 registers)
+constexpr int kTsfZPerBlock = 4;   // warps per block, one inducing tensor each
 constexpr int kTsfSeqPerThread = 2;
 
 template <bool RBF, int NLEV, int DPA>
 __global__ void __launch_bounds__(kTsfZPerBlock * 32) tens_seq_fast_kernel(const TsfFastParams p) {
     constexpr int T = NLEV * (NLEV + 1) / 2, H = DPA / 2, NS = kTsfSeqPerThread;
-    extern __shared__ __align__(16) float szf[];  // [warp][T][ninc'][DPA]; LINEAR stores dz (ninc' = 1)
+    // per warp: [T][nst][DPA] then [T] floats; LINEAR stores dz (nst = 1); RBF with increments stores z^0 and 2 dz, and
+    // -|dz|^2 in the trailing array
+    extern __shared__ __align__(16) float szf[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ninc = p.increments ? 2 : 1;
-    const int nst = (RBF && p.increments) ? 2 : 1;  // points kept per component in shared memory
+    const int nst = (RBF && p.increments) ? 2 : 1;  // vectors kept per component in shared memory
     const long long z = (long long)blockIdx.y * kTsfZPerBlock + warp;
     const bool zok = z < p.nz;
-    float* sz = szf + (size_t)warp * T * nst * DPA;
+    const int per_warp = T * nst * DPA + ((T + 3) & ~3);
+    float* sz = szf + (size_t)warp * per_warp;
+    float* snd = sz + T * nst * DPA;
+    float zmax = 0.f;
     if (zok) {
         for (int e = lane; e < T * nst * DPA; e += 32) {
             const int k = e / (nst * DPA), r = e - k * nst * DPA, w = r / DPA, c = r - w * DPA;
             const float* src = p.Z + (((long long)k * p.nz + z) * ninc) * DPA;
             float v;
-            if (!RBF && p.increments) v = src[DPA + c] - src[c];  // dz
-            else v = src[w * DPA + c];
+            if (p.increments) {
+                const float dz = src[DPA + c] - src[c];
+                v = RBF ? (w == 0 ? src[c] : dz + dz) : dz;
+            } else {
+                v = src[c];
+            }
             sz[e] = v;
         }
+        if (RBF && p.increments) {
+            for (int k = lane; k < T; k += 32) {
+                const float* src = p.Z + (((long long)k * p.nz + z) * 2) * DPA;
+                float acc = 0.f;
+                for (int c = 0; c < DPA; ++c) { const float dz = src[DPA + c] - src[c]; acc = fmaf(dz, dz, acc); }
+                snd[k] = -acc;
+                zmax = fmaxf(zmax, acc);
+            }
+        }
     }
+    for (int o = 16; o > 0; o >>= 1) zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
+    const bool zjump = zmax > kWfJumpThreshold;  // warp-uniform
     __syncwarp();
     long long nn[NS];
     bool nok[NS];
@@ -280,10 +306,6 @@ __global__ void __launch_bounds__(kTsfZPerBlock * 32) tens_seq_fast_kernel(const
                 dst[a][2 * h4] = make_float2(v.x, v.y);
                 dst[a][2 * h4 + 1] = make_float2(v.z, v.w);
             }
-            if (RBF) {  // sequence side of the augmented product: (..., 1, -|x|^2/2)
-                const float2 q = dst[a][H - 2];
-                dst[a][H - 2] = make_float2(q.y, q.x);
-            }
         }
     };
     fetch(0, xnext);
@@ -303,37 +325,67 @@ __global__ void __launch_bounds__(kTsfZPerBlock * 32) tens_seq_fast_kernel(const
 #pragma unroll
             for (int pi = 0; pi < m; ++pi, ++k) {
                 float v[NS];
-                if (RBF && nst == 2) {
-                    float2 z0[H], z1[H];
-                    const float4* zp = reinterpret_cast<const float4*>(sz + (k * 2) * DPA);
-#pragma unroll
-                    for (int h4 = 0; h4 < DPA / 4; ++h4) {
-                        const float4 u0 = zp[h4], u1 = zp[DPA / 4 + h4];
-                        z0[2 * h4] = make_float2(u0.x, u0.y); z0[2 * h4 + 1] = make_float2(u0.z, u0.w);
-                        z1[2 * h4] = make_float2(u1.x, u1.y); z1[2 * h4 + 1] = make_float2(u1.z, u1.w);
-                    }
-#pragma unroll
-                    for (int a = 0; a < NS; ++a) {
-                        float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
-#pragma unroll
-                        for (int h = 0; h < H; ++h) { a0 = __ffma2_rn(z0[h], x[a][h], a0); a1 = __ffma2_rn(z1[h], x[a][h], a1); }
-                        v[a] = tsf_ex2(a1.x + a1.y) - tsf_ex2(a0.x + a0.y);
-                    }
-                } else {
-                    float2 z0[H];
-                    const float4* zp = reinterpret_cast<const float4*>(sz + k * DPA);
+                float2 z0[H];
+                {
+                    const float4* zp = reinterpret_cast<const float4*>(sz + (k * nst) * DPA);
 #pragma unroll
                     for (int h4 = 0; h4 < DPA / 4; ++h4) {
                         const float4 u0 = zp[h4];
                         z0[2 * h4] = make_float2(u0.x, u0.y); z0[2 * h4 + 1] = make_float2(u0.z, u0.w);
                     }
+                }
+                if (RBF) {
+                    float2 w[NS][H];
+                    float nw[NS];
 #pragma unroll
                     for (int a = 0; a < NS; ++a) {
-                        float2 a0 = make_float2(0.f, 0.f);
 #pragma unroll
-                        for (int h = 0; h < H; ++h) a0 = __ffma2_rn(z0[h], x[a][h], a0);
-                        const float d0 = a0.x + a0.y;
-                        v[a] = RBF ? tsf_ex2(d0) : d0;
+                        for (int h = 0; h < H; ++h) w[a][h] = __fadd2_rn(x[a][h], make_float2(-z0[h].x, -z0[h].y));
+                        float2 ww = __fmul2_rn(w[a][0], w[a][0]);
+#pragma unroll
+                        for (int h = 1; h < H; ++h) ww = __ffma2_rn(w[a][h], w[a][h], ww);
+                        nw[a] = ww.x + ww.y;
+                        v[a] = tsf_ex2(-nw[a]);
+                    }
+                    if (nst == 2) {
+                        float2 d2[H];
+                        const float4* zp = reinterpret_cast<const float4*>(sz + (k * 2 + 1) * DPA);
+#pragma unroll
+                        for (int h4 = 0; h4 < DPA / 4; ++h4) {
+                            const float4 u1 = zp[h4];
+                            d2[2 * h4] = make_float2(u1.x, u1.y); d2[2 * h4 + 1] = make_float2(u1.z, u1.w);
+                        }
+                        const float nd = snd[k];
+                        if (!zjump) {
+#pragma unroll
+                            for (int a = 0; a < NS; ++a) {
+                                float2 acc = make_float2(nd - nw[a], 0.f);
+#pragma unroll
+                                for (int h = 0; h < H; ++h) acc = __ffma2_rn(w[a][h], d2[h], acc);
+                                v[a] = tsf_ex2(acc.x + acc.y) - v[a];
+                            }
+                        } else {
+                            const float2 mh = make_float2(-0.5f, -0.5f);
+#pragma unroll
+                            for (int a = 0; a < NS; ++a) {
+                                float2 w1 = __ffma2_rn(d2[0], mh, w[a][0]);
+                                float2 ww = __fmul2_rn(w1, w1);
+#pragma unroll
+                                for (int h = 1; h < H; ++h) {
+                                    w1 = __ffma2_rn(d2[h], mh, w[a][h]);
+                                    ww = __ffma2_rn(w1, w1, ww);
+                                }
+                                v[a] = tsf_ex2(-(ww.x + ww.y)) - v[a];
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int a = 0; a < NS; ++a) {
+                        float2 a0 = __fmul2_rn(z0[0], x[a][0]);
+#pragma unroll
+                        for (int h = 1; h < H; ++h) a0 = __ffma2_rn(z0[h], x[a][h], a0);
+                        v[a] = a0.x + a0.y;
                     }
                 }
 #pragma unroll
@@ -366,7 +418,7 @@ template <bool RBF, int NLEV, int DPA>
 static int launch_tsf_fast_inst(const TsfFastParams& p, cudaStream_t st) {
     constexpr int T = NLEV * (NLEV + 1) / 2;
     const int nst = (RBF && p.increments) ? 2 : 1;
-    const size_t smem = (size_t)kTsfZPerBlock * T * nst * DPA * sizeof(float);
+    const size_t smem = (size_t)kTsfZPerBlock * (T * nst * DPA + ((T + 3) & ~3)) * sizeof(float);
     dim3 grid((unsigned)((p.n + 32 * kTsfSeqPerThread - 1) / (32 * kTsfSeqPerThread)),
               (unsigned)((p.nz + kTsfZPerBlock - 1) / kTsfZPerBlock));
     ProfScope prof(GPSIG_PROF_TENS, st, (double)p.nz * p.n);
@@ -393,10 +445,10 @@ static int launch_tsf_fast_lev(int nlev, const TsfFastParams& p, cudaStream_t st
 static int launch_tsf_fast(bool rbf, int nlev, int DPA, const TsfFastParams& p, cudaStream_t st) {
     if (rbf) {
         switch (DPA) {
+            case 4: return launch_tsf_fast_lev<true, 4>(nlev, p, st);
             case 8: return launch_tsf_fast_lev<true, 8>(nlev, p, st);
             case 12: return launch_tsf_fast_lev<true, 12>(nlev, p, st);
             case 16: return launch_tsf_fast_lev<true, 16>(nlev, p, st);
-            case 20: return launch_tsf_fast_lev<true, 20>(nlev, p, st);
         }
     } else {
         switch (DPA) {
@@ -472,16 +524,16 @@ extern "C" int gpsig_tens_seq_kern_levels(int kind, const float* params, const f
                       !(kind == GPSIG_KERN_LINEAR && difference && L < 2);
     if (fast) {
         const bool rbf = kind == GPSIG_KERN_RBF;
-        const int DPA = rbf ? DP + 4 : DP;
-        const int xmode = rbf ? 2 : (difference ? 1 : 0);
+        const int DPA = DP;
+        const int xmode = rbf ? 3 : (difference ? 1 : 0);
         const int rowsX = xmode == 1 ? L - 1 : L;
         float* fb = nullptr;
         cudaError_t fe = cudaMallocAsync((void**)&fb, (size_t)(zpts + xpts) * DPA * sizeof(float), st);
         if (fe != cudaSuccess) return (int)fe;
         float* Zs = fb;
         float* Xs = Zs + zpts * DPA;
-        int frc = launch_prep_points(Z, zpts, 1, d, inv_lengthscales, rbf ? 2 : 0, DPA, Zs, nullptr, st, X);
-        if (!frc) frc = launch_prep_points(X, n, L, d, inv_lengthscales, xmode, DPA, Xs, nullptr, st, X);
+        int frc = launch_prep_points(Z, zpts, 1, d, inv_lengthscales, rbf ? 3 : 0, DPA, Zs, nullptr, st);
+        if (!frc) frc = launch_prep_points(X, n, L, d, inv_lengthscales, xmode, DPA, Xs, nullptr, st);
         if (!frc) {
             TsfFastParams fp;
             fp.Z = Zs; fp.X = Xs; fp.nz = nz; fp.n = n; fp.rowsX = rowsX;

@@ -1,46 +1,54 @@
-// warpfused.cu -- K(X, X) / K(X, X2) level stacks with every warp computing AND consuming its own increment-Gram rows:
-// no HBM intermediate, no shared-memory ring, no barriers between warps (second design; fused.cu
-// holds the first, producer/consumer-split one).
+// warpfused.cu -- K(X, X) / K(X, X2) / Kdiag level stacks with every warp computing AND consuming its own increment-Gram
+// rows: no HBM intermediate, no shared-memory ring, no barriers between warps.  Replaces
+// kernels.py:225-230 (static-kernel Gram) + signature_algs.py:26 (2-D increment) + :28-33 (all levels) in ONE launch.
 //
 // One persistent CTA per SM; each warp owns an independent stream of work items.  An item is G = 32 / LP neighbouring
-// pairs (i, j0..j0+G-1); LP lanes cooperate on one pair and lane l owns the 8-COLUMN strip t in [8 l, 8 l + 8): its 8
-// points of the column sequence y_j live in registers for the whole item (RBF: the strip of increment columns is shifted
-// left by one so that the halo value comes from lane l - 1, which is one row AHEAD in the skew), A_m[s, t] of all levels
-// too (32 registers at M = 5 -- half of the 16-column strips of sigstream.cu, which is what lets the Gram arithmetic
-// fit beside the recursion).  Lanes run skewed by one row exactly as in sigstream.cu: at step T lane l evaluates the
-// increments Delta[T - l, strip l] (packed fma.rn.f32x2 dot products against the row point x_i[T - l] read from the
-// warp's shared-memory tile; RBF: ex2.approx of the augmented product, then the 2-D increment against the previous
-// row's values) and immediately feeds them to
+// pairs (i, j0..j0+G-1); LP lanes cooperate on one pair and lane l owns the 8-COLUMN strip of points t in [8 l, 8 l + 8):
+// everything it needs of the column sequence y_j lives in registers for the whole item, A_m[s, t] of all levels too.
+// Lanes run skewed by one row: at step T lane l evaluates the increments Delta[T - l, strip l] against the row point
+// x_i[T - l] (read from the warp's shared-memory tile) and immediately feeds them to
 //         A_m[r+1, t] = A_m[r, t] + p_m ;   p_m += Delta[r, t] * A_{m-1}[r, t]
 // with the running row prefix p_m arriving from the left strip by one shfl.up per level.  The row stream never stops at
 // item boundaries.  Per item the warp stages two small tiles itself (coalesced loads, __syncwarp only): x_i (double
-// buffered: strips cross the item boundary at different steps) and the y_j of its G pairs (each lane copies its
-// points from there when ITS strip starts the item).  Arithmetic per entry is the same as gram.cu + sigstream.cu, so the
-// results are bit-identical to the two-kernel path.
+// buffered: strips cross the item boundary at different steps) and the y_j of its G pairs (each lane copies its points
+// from there when ITS strip starts the item).
 //
-// Measured alternatives (round 1, K(X,X) N=4096 L=128 d=8 M=5): 4-column strips (half the state, 16 warps) 214 ms
-// Linear / 267 ms RBF -- the 32 distinct x rows per load and twice the shuffles per entry cost more than the extra warps
-// give; padding the x tile against the 2-way bank conflict of the row reads costs a warp of shared memory (165-171 ms);
-// fewer warps: 10 -> 188 ms, 8 -> 190 ms.  Splitting the step loop into the LP "event" steps of an item period and
-// Lrow - LP test-free steps left Linear at 153 ms (12 warps, FMA-pipe / latency bound) but took RBF from 231 to 188 ms
-// (8 warps: the branches were what kept its two warps per scheduler from overlapping).
-#include <stdlib.h>
-
+// Static kernels (MODE):
+//   0 LINEAR  prepared data = scaled time increments; Delta[s, t] = <dx_s, dy_t> (bilinearity of kernels.py:802 + :26).
+//   1 RBF, anchored form.  Points are scaled so that log2 k(x, y) = -|x - y|^2.  Every strip has a LOCAL anchor a (its
+//     point number 3): with w = x_s - a (once per row) and u_t = y_t - a (once per item),
+//         -|x_s - y_t|^2 = -|w|^2 + 2 <w, u_t> - |u_t|^2,
+//     i.e. one packed dot product per entry like the textbook expansion, but every term is bounded by the distance of
+//     the two points to something next to y_t: the fp32 error is ~1e-7 (|w| + |u|)^2 relative to k, and k underflows
+//     long before |w| matters.  No global centre, no dependence on where the data sits (round 1 centred the expansion on
+//     X[0, 0, :]: 4e-4 errors 30 lengthscales away).  The anchor column itself costs the plain |w|^2.
+//   2 RBF, direct form sum_c (x_c - y_c)^2: used instead of mode 1 when some strip of the call has |u_t|^2 above
+//     kWfJumpThreshold (a path that jumps several lengthscales within 4 steps), decided ON THE DEVICE: the prep kernel
+//     leaves max |u|^2 in a flag word, both instantiations are launched and the one that does not apply returns at once.
+// The recursion is identical in all modes (2 FP32 operations per entry per level).
+//
+// Rows are given as a LIST of row blocks (multi-GPU shards own several, parallel.py) processed by one launch.
 #include <type_traits>
 
 #include "internal.cuh"
 
 namespace gpsig {
 
-constexpr int kWfCols = 8;  // columns per lane strip
+constexpr int kWfCols = 8;    // points per lane strip
+constexpr int kWfAnchor = 3;  // strip-local anchor point (RBF mode 1)
 
 struct WfParams {
-    const float* A;   // prepared row-side points / increments    (rows i, rowsA, DPA)
-    const float* B;   // prepared column-side points / increments (rows j, rowsB, DPA)
-    int rowsA, rowsB; // rowsA == stream rows per item (RBF: row 0 only primes the differencing)
-    int P;            // padded columns per pair = 8 LP
-    int LP, log2LP, G, njg;
-    int n1, n2, upper_only, i_off, j_off;
+    const float* A;   // prepared row-side data    (rows i, rowsA, D)
+    const float* B;   // prepared column-side data (rows j, rowsB, D)
+    const unsigned* flag;  // RBF: float bits of max |u|^2 over the column side (NULL = never jumpy)
+    int rowsA, rowsB;      // rowsA == steps per item (RBF: row 0 only primes the differencing)
+    int LP, log2LP, G;
+    int NJG;               // column groups of the whole problem (global numbering)
+    int n2, upper_only, diag;
+    int nblk;
+    int blk_begin[kWfMaxRowBlocks], blk_end[kWfMaxRowBlocks];   // global row ranges
+    long long blk_out_row[kWfMaxRowBlocks];                      // output row of blk_begin
+    long long blk_items0[kWfMaxRowBlocks + 1];                   // items before the block
     long long nitems;
     int NW;
     long long ldo;
@@ -55,44 +63,65 @@ __device__ __forceinline__ float wf_ex2(float x) {
     return y;
 }
 
-struct WfTrack { int i, rel, cnt; };  // item -> row i, position of its group among the groups row i keeps
+// item -> (row block, row i, position of its group among the groups row i keeps)
+struct WfTrack { int blk, i, rel, cnt; };
 
+__device__ __forceinline__ int wf_first_group(const WfParams& p, int i) { return p.upper_only ? i / p.G : 0; }
+// items of rows [b, i) of a block starting at global row b
+__device__ __forceinline__ long long wf_items_rows(const WfParams& p, int b, int i) {
+    long long n = (long long)(i - b) * p.NJG;
+    if (p.upper_only) n -= tri_floor(i, p.G) - tri_floor(b, p.G);
+    return n;
+}
 __device__ __forceinline__ void wf_track_init(const WfParams& p, WfTrack& t, long long u) {
-    int i, jg;
-    if (!p.upper_only) {
-        i = (int)(u / p.njg);
-        jg = (int)(u - (long long)i * p.njg);
-    } else {
-        int lo = 0, hi = p.n1 - 1;
-        while (lo < hi) {
-            int mid = (lo + hi + 1) >> 1;
-            if (items_before(mid, p.njg, p.G, 1, p.i_off, p.j_off) <= u) lo = mid; else hi = mid - 1;
-        }
-        i = lo;
-        jg = (int)(u - items_before(lo, p.njg, p.G, 1, p.i_off, p.j_off)) + first_group(lo, p.G, 1, p.i_off, p.j_off);
+    int k = 0;
+    while (k + 1 < p.nblk && p.blk_items0[k + 1] <= u) ++k;
+    const long long v = u - p.blk_items0[k];
+    int lo = p.blk_begin[k], hi = p.blk_end[k] - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (wf_items_rows(p, p.blk_begin[k], mid) <= v) lo = mid; else hi = mid - 1;
     }
-    const int fg = first_group(i, p.G, p.upper_only, p.i_off, p.j_off);
-    t.i = i; t.rel = jg - fg; t.cnt = p.njg - fg;
+    t.blk = k; t.i = lo;
+    t.rel = (int)(v - wf_items_rows(p, p.blk_begin[k], lo));
+    t.cnt = p.NJG - wf_first_group(p, lo);
 }
 __device__ __forceinline__ void wf_track_next(const WfParams& p, WfTrack& t) {
     t.rel += p.NW;
-    while (t.rel >= t.cnt && t.i + 1 < p.n1) {
+    while (t.rel >= t.cnt) {
+        int ni = t.i + 1, nb = t.blk;
+        if (ni >= p.blk_end[nb]) {
+            if (nb + 1 >= p.nblk) break;  // past the last item: stays put (never staged, never written)
+            ++nb;
+            ni = p.blk_begin[nb];
+        }
         t.rel -= t.cnt;
-        ++t.i;
-        t.cnt = p.njg - first_group(t.i, p.G, p.upper_only, p.i_off, p.j_off);
+        t.i = ni; t.blk = nb;
+        t.cnt = p.NJG - wf_first_group(p, ni);
     }
 }
-__device__ __forceinline__ int wf_track_jg(const WfParams& p, const WfTrack& t) {
-    return t.rel + first_group(t.i, p.G, p.upper_only, p.i_off, p.j_off);
-}
+__device__ __forceinline__ int wf_track_jg(const WfParams& p, const WfTrack& t) { return t.rel + wf_first_group(p, t.i); }
 
-// DPA = floats per prepared point; HU = leading float2 pairs that carry data (DPA/2 LINEAR, DPA/2 - 1 RBF)
-template <bool RBF, int NLEV, int DPA, int HU, int MAXW>
+// D = floats per prepared point (4 or 8)
+//
+// Issue slots, not only the FP32 pipe, bound this kernel (B200: packed f32x2 instructions issue once but occupy the FMA
+// pipe for two cycles -- tools/ubench/pipes.cu), so everything that pairs naturally is packed: the level state is kept
+// as float2 pairs (A_{2i}, A_{2i+1}) and (p_{2i}, p_{2i+1}), which turns the NLEV - 1 adds of A_m += p_m into half as many
+// add.f32x2; the row differencing and the level sums likewise.  The p_m updates stay scalar FFMAs (their operands pair
+// up with the OTHER parity).
+template <int MODE, int NLEV, int D, int MAXW>
 __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_warpfused_kernel(const WfParams p) {
+    constexpr bool RBF = MODE != 0;
+    constexpr int NA = NLEV - 1;        // A_0 .. A_{NA-1}
+    constexpr int NAP = NA / 2;         // pairs of A levels (+ one scalar level if NA is odd)
+    constexpr int NPP = NLEV / 2;       // pairs of p levels (+ one scalar level if NLEV is odd)
+    constexpr int W = kWfCols, H = D / 2, C4 = D / 4;
+    static_assert(NLEV >= 2 && NLEV <= 6, "levels");
+    if (RBF) {  // exactly one of the two RBF instantiations does the work of a call
+        const bool jumpy = p.flag != nullptr && __uint_as_float(*p.flag) > kWfJumpThreshold;
+        if (jumpy != (MODE == 2)) return;
+    }
     extern __shared__ __align__(16) float wsm[];
-    constexpr int NA = NLEV > 1 ? NLEV - 1 : 1;
-    constexpr int W = kWfCols;
-    constexpr int NPT = W;
     const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Lrow = p.rowsA, LP = p.LP;
     const long long wg = (long long)blockIdx.x * nwarps + warp;
@@ -100,35 +129,51 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_warpfused_kernel(const W
     const long long total = nloc * Lrow;
     if (total == 0) return;
     const long long nsteps = total + LP - 1;
-    float* xt = wsm + (size_t)warp * (2 * p.xfloats + p.yfloats);  // x tile, two buffers
+    float* xt = wsm + (size_t)warp * (2 * p.xfloats + p.yfloats);  // x tile, two buffers (diag: G sequences each)
     float* yt = xt + 2 * p.xfloats;                                 // y tile of the item strip 0 entered last
     const int l = lane & (LP - 1), q = lane >> p.log2LP;
     const int t0 = l * W;
+    const int xq = p.diag ? q * Lrow * D : 0;  // diag: pair q reads its own row sequence
+    const bool first = l == 0;
 
-    float A[NA][W];
-    float psum[NLEV], ksum[NLEV];
-    float2 y[NPT][HU];
-    float fprev[NPT];
-    float f7 = 0.f, flprev = 0.f;  // RBF: this lane's last column value of the previous step / left-halo value of the previous row
+    float2 AP[NAP > 0 ? NAP : 1][W];
+    float AS[W];                        // level NA - 1 when NA is odd
+    float2 PP[NPP], KP[NPP];
+    float PS = 0.f, KS = 0.f;           // level NLEV - 1 when NLEV is odd
+    float2 y[W][H];      // LINEAR: dy_t;  RBF anchored: 2 (y_t - a);  RBF direct: -y_t
+    float2 nanc[H];      // RBF anchored: minus the anchor a
+    float nu[W];         // RBF anchored: -|y_t - a|^2
+    float2 gprev[W / 2]; // RBF: column differences f[s-1, t] - f[s-1, t-1] of the previous row
+    float flast = 0.f;   // RBF: this lane's last column value of the previous step (the right neighbour's left halo)
 #pragma unroll
-    for (int m = 0; m < NLEV; ++m) { psum[m] = 0.f; ksum[m] = 0.f; }
+    for (int i = 0; i < NPP; ++i) { PP[i] = make_float2(0.f, 0.f); KP[i] = make_float2(0.f, 0.f); }
 #pragma unroll
-    for (int m = 0; m < NA; ++m)
+    for (int j = 0; j < W; ++j) {
+        AS[j] = 0.f;
 #pragma unroll
-        for (int j = 0; j < W; ++j) A[m][j] = 0.f;
-#pragma unroll
-    for (int u = 0; u < NPT; ++u) {
-        fprev[u] = 0.f;
-#pragma unroll
-        for (int h = 0; h < HU; ++h) y[u][h] = make_float2(0.f, 0.f);
+        for (int i = 0; i < NAP; ++i) AP[i][j] = make_float2(0.f, 0.f);
     }
+#pragma unroll
+    for (int u = 0; u < W; ++u) {
+        nu[u] = 0.f;
+#pragma unroll
+        for (int h = 0; h < H; ++h) y[u][h] = make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < W / 2; ++u) gprev[u] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int h = 0; h < H; ++h) nanc[h] = make_float2(0.f, 0.f);
+
+    // scalar views of the paired level state (indices are compile-time constants after unrolling)
+    auto Pm = [&](int m) -> float& { return m < 2 * NPP ? ((m & 1) ? PP[m >> 1].y : PP[m >> 1].x) : PS; };
+    auto Am = [&](int m, int j) -> float& { return m < 2 * NAP ? ((m & 1) ? AP[m >> 1][j].y : AP[m >> 1][j].x) : AS[j]; };
 
     WfTrack tx, ty;      // item whose tiles are staged next (warp-uniform) / item this lane works on
     wf_track_init(p, tx, wg);
     ty = tx;
     int s = -l;          // row of this lane's current item (negative: not started)
     int par = 0;         // x-tile buffer of this lane's current item
-    int par0 = 0;        // x-tile buffer of strip 0's item (warp-uniform)
+    int par0 = 0;        // x-tile buffer the next staging fills (warp-uniform)
 
     // CHECK: lanes may be outside their stream (first LP - 1 and last LP - 1 steps of the warp).  EV: the step lies in the
     // first LP steps of an item period, where things happen -- strip 0 stages the tiles (`stage`), every strip copies its
@@ -141,117 +186,224 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_warpfused_kernel(const W
         if (EV && stage) {
             const int i = tx.i, jg0 = wf_track_jg(p, tx) * p.G;
             wf_track_next(p, tx);
-            const float4* srcx = reinterpret_cast<const float4*>(p.A + (long long)(p.i_off + i) * p.rowsA * DPA);
-            float4* dstx = reinterpret_cast<float4*>(xt + par0 * p.xfloats);  // par0 flips after the fill
-            for (int e = lane; e < p.rowsA * (DPA / 4); e += 32) dstx[e] = __ldg(srcx + e);
-            float4* dsty = reinterpret_cast<float4*>(yt);
-            const int per = p.rowsB * (DPA / 4);
-            for (int g = 0; g < p.G; ++g) {
-                int jl = jg0 + g;
-                if (jl > p.n2 - 1) jl = p.n2 - 1;  // padding pair of a ragged last group
-                const float4* srcy = reinterpret_cast<const float4*>(p.B + (long long)(p.j_off + jl) * p.rowsB * DPA);
-                for (int e = lane; e < per; e += 32) dsty[g * per + e] = __ldg(srcy + e);
+            float4* dstx = reinterpret_cast<float4*>(xt + par0 * p.xfloats);
+            const int perx = Lrow * C4;
+            const int nx = p.diag ? p.G : 1;
+            for (int g = 0; g < nx; ++g) {
+                int src_seq = i;
+                if (p.diag) { src_seq = jg0 + g; if (src_seq > p.n2 - 1) src_seq = p.n2 - 1; }
+                const float4* srcx = reinterpret_cast<const float4*>(p.A + (long long)src_seq * Lrow * D);
+                for (int e = lane; e < perx; e += 32) {
+                    // D == 8: the two 16-byte halves of a row swap places every 4 rows, which makes the skewed row reads
+                    // (lane l reads row T - l) conflict free
+                    const int row = e / C4, c = e - row * C4;
+                    const int pc = (C4 == 2) ? (c ^ ((row >> 2) & 1)) : c;
+                    dstx[g * perx + row * C4 + pc] = __ldg(srcx + e);
+                }
+            }
+            if (!p.diag) {
+                float4* dsty = reinterpret_cast<float4*>(yt);
+                const int per = p.rowsB * C4;
+                for (int g = 0; g < p.G; ++g) {
+                    int jl = jg0 + g;
+                    if (jl > p.n2 - 1) jl = p.n2 - 1;  // padding pair of a ragged last group
+                    const float4* srcy = reinterpret_cast<const float4*>(p.B + (long long)jl * p.rowsB * D);
+                    for (int e = lane; e < per; e += 32) dsty[g * per + e] = __ldg(srcy + e);
+                }
             }
             __syncwarp();
             par0 ^= 1;
         }
+        // a strip that finished its item on the previous step moves on (always within the EV steps: strip l finishes at
+        // period step l - 1, strip 0 on the last step of the period)
+        if (EV && s == Lrow) { s = 0; par ^= 1; wf_track_next(p, ty); }
         const bool valid = CHECK ? (s >= 0 && T - l < total) : true;
         // ---- this strip enters the item: its column points move from the tile into registers ----
         if (EV && valid && s == 0) {
+            if (MODE == 1) {
+                int ta = t0 + kWfAnchor;
+                if (ta > p.rowsB - 1) ta = p.rowsB - 1;
+                if (p.diag) {
+                    const float4* src = reinterpret_cast<const float4*>(xt + par * p.xfloats + xq) + ta * C4;
+                    const int sw = (C4 == 2) ? ((ta >> 2) & 1) : 0;
 #pragma unroll
-            for (int u = 0; u < NPT; ++u) {
-                const int t = t0 + u;
-                const bool ok = RBF || t < p.rowsB;
-                const int tc = t < p.rowsB ? t : p.rowsB - 1;
-                const float2* src = reinterpret_cast<const float2*>(yt + ((size_t)q * p.rowsB + tc) * DPA);
+                    for (int c = 0; c < C4; ++c) {
+                        const float4 v = src[c ^ sw];
+                        nanc[2 * c] = make_float2(-v.x, -v.y);
+                        nanc[2 * c + 1] = make_float2(-v.z, -v.w);
+                    }
+                } else {
+                    const float2* src = reinterpret_cast<const float2*>(yt + ((size_t)q * p.rowsB + ta) * D);
 #pragma unroll
-                for (int h = 0; h < HU; ++h) y[u][h] = ok ? src[h] : make_float2(0.f, 0.f);
-                if (RBF) {  // column side of the augmented product: (..., 1, -|y|^2/2)
-                    const float2 a = y[u][HU - 1];
-                    y[u][HU - 1] = make_float2(a.y, a.x);
+                    for (int h = 0; h < H; ++h) nanc[h] = make_float2(-src[h].x, -src[h].y);
                 }
             }
 #pragma unroll
-            for (int m = 0; m < NLEV; ++m) ksum[m] = 0.f;
+            for (int u = 0; u < W; ++u) {
+                const int t = t0 + u;
+                const bool ok = RBF || t < p.rowsB;          // LINEAR: increments past the end are zero
+                const int tc = t < p.rowsB ? t : p.rowsB - 1;  // RBF: clamp (equal points difference to exactly zero)
+                float2 raw[H];
+                if (p.diag) {
+                    const float4* src = reinterpret_cast<const float4*>(xt + par * p.xfloats + xq) + tc * C4;
+                    const int sw = (C4 == 2) ? ((tc >> 2) & 1) : 0;
 #pragma unroll
-            for (int m = 0; m < NA; ++m)
+                    for (int c = 0; c < C4; ++c) {
+                        const float4 v = src[c ^ sw];
+                        raw[2 * c] = make_float2(v.x, v.y);
+                        raw[2 * c + 1] = make_float2(v.z, v.w);
+                    }
+                } else {
+                    const float2* src = reinterpret_cast<const float2*>(yt + ((size_t)q * p.rowsB + tc) * D);
 #pragma unroll
-                for (int j = 0; j < W; ++j) A[m][j] = 0.f;
+                    for (int h = 0; h < H; ++h) raw[h] = src[h];
+                }
+                if (MODE == 1) {
+                    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int h = 0; h < H; ++h) {
+                        const float2 df = make_float2(raw[h].x + nanc[h].x, raw[h].y + nanc[h].y);
+                        acc = __ffma2_rn(df, df, acc);
+                        y[u][h] = make_float2(df.x + df.x, df.y + df.y);
+                    }
+                    nu[u] = -(acc.x + acc.y);
+                } else if (MODE == 2) {
+#pragma unroll
+                    for (int h = 0; h < H; ++h) y[u][h] = make_float2(-raw[h].x, -raw[h].y);
+                } else {
+#pragma unroll
+                    for (int h = 0; h < H; ++h) y[u][h] = ok ? raw[h] : make_float2(0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NPP; ++i) KP[i] = make_float2(0.f, 0.f);
+            KS = 0.f;
+#pragma unroll
+            for (int j = 0; j < W; ++j) {
+                AS[j] = 0.f;
+#pragma unroll
+                for (int i = 0; i < NAP; ++i) AP[i][j] = make_float2(0.f, 0.f);
+            }
         }
         // running row prefixes arrive from the strip to the left (it finished this row one step ago)
         float pin[NLEV];
 #pragma unroll
         for (int m = 0; m < NLEV; ++m) {
-            pin[m] = __shfl_up_sync(0xffffffffu, psum[m], 1);
-            if (l == 0) pin[m] = 0.f;
+            pin[m] = __shfl_up_sync(0xffffffffu, Pm(m), 1);
+            if (first) pin[m] = 0.f;
         }
         float fl = 0.f;
-        if (RBF) fl = __shfl_up_sync(0xffffffffu, f7, 1);
+        if (RBF) fl = __shfl_up_sync(0xffffffffu, flast, 1);
         // ---- increments of row s of the strip ----
-        float d[W];
+        float2 d2[W / 2];
 #pragma unroll
-        for (int u = 0; u < W; ++u) d[u] = 0.f;
+        for (int u = 0; u < W / 2; ++u) d2[u] = make_float2(0.f, 0.f);
         if (valid) {
-            const float2* xs = reinterpret_cast<const float2*>(xt + par * p.xfloats + (size_t)s * DPA);
-            float2 x[HU];
+            float2 x[H];
+            {
+                const float4* xs = reinterpret_cast<const float4*>(xt + par * p.xfloats + xq) + s * C4;
+                const int sw = (C4 == 2) ? ((s >> 2) & 1) : 0;
 #pragma unroll
-            for (int h = 0; h < HU; ++h) x[h] = xs[h];
-            float f[NPT];
-#pragma unroll
-            for (int u = 0; u < NPT; ++u) {
-                float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int h = 0; h < HU; ++h) acc = __ffma2_rn(x[h], y[u][h], acc);
-                const float v = acc.x + acc.y;
-                f[u] = RBF ? wf_ex2(v) : v;
+                for (int c = 0; c < C4; ++c) {
+                    const float4 v = xs[c ^ sw];
+                    x[2 * c] = make_float2(v.x, v.y);
+                    x[2 * c + 1] = make_float2(v.z, v.w);
+                }
             }
-            if (RBF) {
+            if (MODE == 0) {
+#pragma unroll
+                for (int u = 0; u < W; ++u) {
+                    float2 acc = __fmul2_rn(x[0], y[u][0]);
+#pragma unroll
+                    for (int h = 1; h < H; ++h) acc = __ffma2_rn(x[h], y[u][h], acc);
+                    if (u & 1) d2[u >> 1].y = acc.x + acc.y; else d2[u >> 1].x = acc.x + acc.y;
+                }
+            } else {
+                float f[W];
+                if (MODE == 1) {
+                    float2 w[H];
+#pragma unroll
+                    for (int h = 0; h < H; ++h) w[h] = __fadd2_rn(x[h], nanc[h]);
+                    float2 ww = __fmul2_rn(w[0], w[0]);
+#pragma unroll
+                    for (int h = 1; h < H; ++h) ww = __ffma2_rn(w[h], w[h], ww);
+                    const float nw = ww.x + ww.y;  // |w|^2
+#pragma unroll
+                    for (int u = 0; u < W; ++u) {
+                        if (u == kWfAnchor) {
+                            f[u] = wf_ex2(-nw);
+                        } else {
+                            float2 acc = make_float2(nu[u] - nw, 0.f);
+#pragma unroll
+                            for (int h = 0; h < H; ++h) acc = __ffma2_rn(w[h], y[u][h], acc);
+                            f[u] = wf_ex2(acc.x + acc.y);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < W; ++u) {
+                        float2 df = __fadd2_rn(x[0], y[u][0]);
+                        float2 acc = __fmul2_rn(df, df);
+#pragma unroll
+                        for (int h = 1; h < H; ++h) {
+                            df = __fadd2_rn(x[h], y[u][h]);
+                            acc = __ffma2_rn(df, df, acc);
+                        }
+                        f[u] = wf_ex2(-(acc.x + acc.y));
+                    }
+                }
                 // lane l owns the increment columns 8 l - 1 .. 8 l + 6 (column -1 is a zero pad): the value to the LEFT of
                 // its first point belongs to lane l - 1, which evaluated this very row one step ago
-                if (!EV || s > 0) {
-                    d[0] = l == 0 ? 0.f : (f[0] - fl) - (fprev[0] - flprev);
+                float2 g[W / 2];
+                g[0] = make_float2(f[0] - fl, f[1] - f[0]);
 #pragma unroll
-                    for (int u = 1; u < W; ++u) d[u] = (f[u] - f[u - 1]) - (fprev[u] - fprev[u - 1]);
+                for (int u = 1; u < W / 2; ++u) g[u] = make_float2(f[2 * u] - f[2 * u - 1], f[2 * u + 1] - f[2 * u]);
+                if (!EV || s > 0) {
+                    const float2 m1 = make_float2(-1.f, -1.f);
+#pragma unroll
+                    for (int u = 0; u < W / 2; ++u) d2[u] = __ffma2_rn(gprev[u], m1, g[u]);
+                    if (first) d2[0].x = 0.f;
                 }
 #pragma unroll
-                for (int u = 0; u < NPT; ++u) fprev[u] = f[u];
-                flprev = fl;
-                f7 = f[W - 1];
-            } else {
-#pragma unroll
-                for (int u = 0; u < W; ++u) d[u] = f[u];
+                for (int u = 0; u < W / 2; ++u) gprev[u] = g[u];
+                flast = f[W - 1];
             }
         }
         // ---- the recursion: 2 FP ops per entry per level ----
 #pragma unroll
-        for (int m = 0; m < NLEV; ++m) psum[m] = pin[m];
+        for (int m = 0; m < NLEV; ++m) Pm(m) = pin[m];
 #pragma unroll
         for (int j = 0; j < W; ++j) {
-            const float dj = d[j];
+            const float dj = (j & 1) ? d2[j >> 1].y : d2[j >> 1].x;
+            float pn[NLEV];  // p_m after this column (levels >= 1 read the OLD A_{m-1} and the OLD p_m)
 #pragma unroll
-            for (int m = NLEV - 1; m >= 1; --m) {
-                const float a_prev = A[m - 1][j];
-                if (m < NLEV - 1) A[m][j] += psum[m];
-                psum[m] = fmaf(dj, a_prev, psum[m]);
-            }
-            if (NLEV > 1) A[0][j] += psum[0];
-            psum[0] += dj;
+            for (int m = 1; m < NLEV; ++m) pn[m] = fmaf(dj, Am(m - 1, j), Pm(m));
+            pn[0] = Pm(0) + dj;
+#pragma unroll
+            for (int i = 0; i < NAP; ++i) AP[i][j] = __fadd2_rn(AP[i][j], PP[i]);
+            if (NA & 1) AS[j] += Pm(NA - 1);
+#pragma unroll
+            for (int m = 0; m < NLEV; ++m) Pm(m) = pn[m];
         }
         if (valid) {
 #pragma unroll
-            for (int m = 0; m < NLEV; ++m) ksum[m] += psum[m];
+            for (int i = 0; i < NPP; ++i) KP[i] = __fadd2_rn(KP[i], PP[i]);
+            if (NLEV & 1) KS += PS;
             if (EV && s == Lrow - 1 && l == LP - 1) {
                 const int j = wf_track_jg(p, ty) * p.G + q;
                 if (j < p.n2) {
-                    float* o = p.out + (long long)(p.i_off + ty.i) * p.ldo + p.j_off + j;
+                    float* o = p.diag ? p.out + j
+                                      : p.out + (p.blk_out_row[ty.blk] + (ty.i - p.blk_begin[ty.blk])) * p.ldo + j;
                     o[0] = 1.f;
 #pragma unroll
-                    for (int m = 0; m < NLEV; ++m) o[(long long)(m + 1) * p.out_level_stride] = ksum[m];
+                    for (int m = 0; m < NLEV; ++m) {
+                        const float kv = m < 2 * NPP ? ((m & 1) ? KP[m >> 1].y : KP[m >> 1].x) : KS;
+                        o[(long long)(m + 1) * p.out_level_stride] = kv;
+                    }
                 }
             }
         }
-        // ---- advance the row counters (the lane's started at -l) ----
-        if (++s == Lrow) { s = 0; par ^= 1; wf_track_next(p, ty); }  // strip 0 wraps on the last step of a period
+        ++s;  // the lane's row counter started at -l
     };
 
     const std::true_type yes{};
@@ -269,6 +421,39 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_warpfused_kernel(const W
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// the jump flag: max over the column side of |y_t - a(strip of t)|^2 in the scaled units of prep mode 3
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void wf_jump_flag_kernel(const float* __restrict__ B, long long n, int rows, int D, unsigned* __restrict__ flag) {
+    const long long total = n * rows;
+    float worst = 0.f;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long seq = idx / rows;
+        const int t = (int)(idx - seq * rows);
+        int ta = (t / kWfCols) * kWfCols + kWfAnchor;
+        if (ta > rows - 1) ta = rows - 1;
+        const float* yp = B + idx * D;
+        const float* ap = B + (seq * rows + ta) * D;
+        float acc = 0.f;
+        for (int c = 0; c < D; ++c) { const float df = yp[c] - ap[c]; acc = fmaf(df, df, acc); }
+        worst = fmaxf(worst, acc);
+    }
+    for (int o = 16; o > 0; o >>= 1) worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+    if ((threadIdx.x & 31) == 0 && worst > 0.f) atomicMax(flag, __float_as_uint(worst));  // non-negative floats order as uints
+}
+
+int launch_wf_jump_flag(const float* B, long long n, int rows, int D, unsigned* flag, bool reset, cudaStream_t st) {
+    if (reset) {
+        cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(unsigned), st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    const long long total = n * rows;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)num_sms() * 8;
+    wf_jump_flag_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(B, n, rows, D, flag);
+    return check_launch();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------------
 static int wf_log2(int x) {
@@ -277,32 +462,28 @@ static int wf_log2(int x) {
     return l;
 }
 
-// lanes per pair for `ncols` increment columns with 8-column strips (>= 2)
-int wf_lanes_per_pair(int ncols) {
-    int need = (ncols + kWfCols - 1) / kWfCols;
+// lanes per pair for `npts` strip points with 8-point strips (>= 2)
+int wf_lanes_per_pair(int npts) {
+    int need = (npts + kWfCols - 1) / kWfCols;
     return 1 << wf_log2(need < 2 ? 2 : need);
 }
 
-// Default path of K(X, X) / K(X, X2) for the shapes it is instantiated for (measured on the headline shape: Linear 153 ms,
-// RBF 188 ms per step against 190-210 / 202-217 ms for producer + stream recursion).  GPSIG_WARPFUSED=0 switches back to
-// the two-kernel pipeline (bench.py does that for its "pipeline" pass).
+// Default path of K(X, X) / K(X, X2) / Kdiag for LINEAR and RBF with d <= 8, 2 <= M <= 5 and sequences of 17..257 points.
+// GPSIG_WARPFUSED=0 (read once, at load) switches back to the two-kernel pipeline (bench.py's "pipeline" pass).
 bool warpfused_supported(bool rbf, int d, int nlev, int ncols, int rowsA) {
-    (void)rbf;
     if (nlev < 2 || nlev > 5 || d > 8) return false;
-    if (ncols + 1 > 32 * kWfCols || rowsA < 48) return false;
-    const char* v = getenv("GPSIG_WARPFUSED");
-    return !(v && *v == '0');
+    const int npts = rbf ? ncols + 1 : ncols;
+    if (npts > 32 * kWfCols) return false;
+    if (rowsA < wf_lanes_per_pair(npts) || rowsA < 16) return false;  // an item period must cover the LP event steps
+    return env_knobs().warpfused != 0;
 }
 
-template <bool RBF, int NLEV, int DPA, int HU, int MAXW>
+template <int MODE, int NLEV, int D, int MAXW>
 static int launch_wf_maxw(WfParams& p, cudaStream_t st) {
-    auto kern = sigkern_warpfused_kernel<RBF, NLEV, DPA, HU, MAXW>;
+    auto kern = sigkern_warpfused_kernel<MODE, NLEV, D, MAXW>;
     const size_t per_warp = (size_t)(2 * p.xfloats + p.yfloats) * sizeof(float);
     int nw = MAXW;
-    {
-        const char* v = getenv("GPSIG_WARPFUSED_WARPS");
-        if (v && *v) { nw = atoi(v); if (nw < 1) nw = 1; if (nw > MAXW) nw = MAXW; }
-    }
+    if (env_knobs().warpfused_warps > 0 && env_knobs().warpfused_warps < nw) nw = env_knobs().warpfused_warps;
     while (nw > 1 && per_warp * nw > 232448) --nw;
     if (per_warp * nw > 232448) return GPSIG_E_UNSUPPORTED;
     const size_t smem = per_warp * nw;
@@ -311,59 +492,66 @@ static int launch_wf_maxw(WfParams& p, cudaStream_t st) {
     p.NW = grid * nw;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    ProfScope prof(GPSIG_PROF_FUSED, st, (double)p.nitems * p.G);
     kern<<<grid, nw * 32, smem, st>>>(p);
     return check_launch();
 }
 
-// register budget per thread: 12 warps -> 168, 8 warps -> 255 (allocation granule: 4 warps).  LINEAR fits 168; RBF needs
-// ~230 (the exponent arguments of 8 points and the previous row's values), so it runs 8 warps per SM (a 12-warp build
-// spills ~400 bytes per thread and was measured at 445 ms against 231 ms)
-template <bool RBF, int NLEV, int DPA, int HU>
-static int launch_wf_inst(WfParams& p, cudaStream_t st) {
-    return launch_wf_maxw<RBF, NLEV, DPA, HU, RBF ? 8 : 12>(p, st);
-}
-
-template <bool RBF, int DPA, int HU>
+// register budget per thread: 12 warps -> 168, 8 warps -> 255 (allocation granule: 4 warps)
+template <int MODE, int D>
 static int launch_wf_lev(int nlev, WfParams& p, cudaStream_t st) {
+    constexpr int MAXW = (MODE == 0 || MODE == 1) ? 12 : 8;
     switch (nlev) {
-        case 2: return launch_wf_inst<RBF, 2, DPA, HU>(p, st);
-        case 3: return launch_wf_inst<RBF, 3, DPA, HU>(p, st);
-        case 4: return launch_wf_inst<RBF, 4, DPA, HU>(p, st);
-        case 5: return launch_wf_inst<RBF, 5, DPA, HU>(p, st);
+        case 2: return launch_wf_maxw<MODE, 2, D, MAXW>(p, st);
+        case 3: return launch_wf_maxw<MODE, 3, D, MAXW>(p, st);
+        case 4: return launch_wf_maxw<MODE, 4, D, MAXW>(p, st);
+        case 5: return launch_wf_maxw<MODE, 5, D, MAXW>(p, st);
     }
     return GPSIG_E_UNSUPPORTED;
 }
 
-// Level stacks of the pair block rows [i_off, i_off + n1) x cols [j_off, j_off + n2) from prepared points (gram.cu prep
-// modes 1 / 2).  `ncols` = increment columns per pair.  Returns GPSIG_E_UNSUPPORTED when there is no instantiation.
-// Rows [i_off, i_off + n1) against all n2_total columns (symmetric: only the groups right of the diagonal); output
-// out[m * lvl_stride + i * ldo + j] with GLOBAL i, j.
-int launch_sigkern_warpfused(bool rbf, const float* A, const float* B, int rowsA, int rowsB, int DPA, int ncols, int n1,
-                             int n2_total, int nlev, int upper_only, int i_off, long long ldo, long long lvl_stride, float* out,
+// Level stacks of the listed row blocks against all n2 columns (symmetric: only the column groups right of the diagonal)
+// from prepared data (gram.cu prep modes 1 / 3).  `npts` = strip points per pair (RBF: ncols + 1, LINEAR: ncols).
+// out[m * lvl_stride + (blk_out_row[k] + i - blk_begin[k]) * ldo + j].  diag != 0: pairs (e, e), out[m * lvl_stride + e].
+// Returns GPSIG_E_UNSUPPORTED when there is no instantiation.
+int launch_sigkern_warpfused(bool rbf, const float* A, const float* B, const unsigned* flag, int rowsA, int rowsB, int D,
+                             int npts, int n2, int nlev, int upper_only, int diag, int nblk, const int* blk_begin,
+                             const int* blk_end, const long long* blk_out_row, long long ldo, long long lvl_stride, float* out,
                              cudaStream_t st) {
-    if (!A || !B || !out || n1 < 1 || n2_total < 1 || rowsA < 1 || rowsB < 1)
+    if (!A || !B || !out || n2 < 1 || rowsA < 1 || rowsB < 1 || nblk < 1)
         return fail(GPSIG_E_BADARG, "sigkern_warpfused: bad sizes");
+    if (nblk > kWfMaxRowBlocks) return fail(GPSIG_E_UNSUPPORTED, "at most %d row blocks per launch", kWfMaxRowBlocks);
     WfParams p;
-    p.A = A; p.B = B; p.rowsA = rowsA; p.rowsB = rowsB;
-    p.LP = wf_lanes_per_pair(rbf ? ncols + 1 : ncols); p.log2LP = wf_log2(p.LP); p.G = 32 / p.LP; p.P = p.LP * kWfCols;
-    const int j_off = upper_only ? (i_off / p.G) * p.G : 0;  // first column group any of these rows keeps
-    const int n2 = n2_total - j_off;
-    p.njg = (n2 + p.G - 1) / p.G;
-    p.n1 = n1; p.n2 = n2; p.upper_only = upper_only ? 1 : 0; p.i_off = i_off; p.j_off = j_off;
-    p.nitems = items_before(n1, p.njg, p.G, p.upper_only, i_off, j_off);
-    p.ldo = ldo; p.out = out; p.out_level_stride = lvl_stride;
-    p.xfloats = rowsA * DPA;
-    p.yfloats = p.G * rowsB * DPA;
-    if (p.nitems < 1) return GPSIG_OK;
-    if (rbf) {
-        if (DPA == 8) return launch_wf_lev<true, 8, 3>(nlev, p, st);
-        if (DPA == 12) return launch_wf_lev<true, 12, 5>(nlev, p, st);
-    } else {
-        if (DPA == 4) return launch_wf_lev<false, 4, 2>(nlev, p, st);
-        if (DPA == 8) return launch_wf_lev<false, 8, 4>(nlev, p, st);
+    p.A = A; p.B = B; p.flag = flag; p.rowsA = rowsA; p.rowsB = rowsB;
+    p.LP = wf_lanes_per_pair(npts); p.log2LP = wf_log2(p.LP); p.G = 32 / p.LP;
+    p.n2 = n2; p.upper_only = upper_only ? 1 : 0; p.diag = diag ? 1 : 0;
+    p.NJG = (n2 + p.G - 1) / p.G;
+    p.nblk = diag ? 1 : nblk;
+    long long items = 0;
+    for (int k = 0; k < p.nblk; ++k) {
+        const int b = diag ? 0 : blk_begin[k], e = diag ? 1 : blk_end[k];
+        if (b < 0 || e <= b) return fail(GPSIG_E_BADARG, "sigkern_warpfused: empty row block");
+        p.blk_begin[k] = b; p.blk_end[k] = e; p.blk_out_row[k] = diag ? 0 : blk_out_row[k];
+        p.blk_items0[k] = items;
+        long long n = (long long)(e - b) * p.NJG;
+        if (p.upper_only) n -= tri_floor(e, p.G) - tri_floor(b, p.G);
+        items += n;
     }
-    return GPSIG_E_UNSUPPORTED;
+    p.blk_items0[p.nblk] = items;
+    p.nitems = items;
+    p.ldo = ldo; p.out = out; p.out_level_stride = lvl_stride;
+    p.xfloats = (diag ? p.G : 1) * rowsA * D;
+    p.yfloats = diag ? 0 : p.G * rowsB * D;
+    if (p.nitems < 1) return GPSIG_OK;
+    ProfScope prof(GPSIG_PROF_FUSED, st, (double)p.nitems * p.G);
+    int rc = GPSIG_E_UNSUPPORTED;
+    if (rbf) {
+        if (D == 4) { rc = launch_wf_lev<1, 4>(nlev, p, st); if (!rc && flag) rc = launch_wf_lev<2, 4>(nlev, p, st); }
+        if (D == 8) { rc = launch_wf_lev<1, 8>(nlev, p, st); if (!rc && flag) rc = launch_wf_lev<2, 8>(nlev, p, st); }
+    } else {
+        if (D == 4) rc = launch_wf_lev<0, 4>(nlev, p, st);
+        if (D == 8) rc = launch_wf_lev<0, 8>(nlev, p, st);
+    }
+    return rc;
 }
 
 }  // namespace gpsig

@@ -177,6 +177,14 @@ class SignatureKernel:
             self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
         return self._ws
 
+    def _workspace_diag(self, dev, n, L, d):
+        lib = _lib.load()
+        need = lib.gpsig_seq_kern_diag_workspace_bytes(n, L, d, 256 << 20)
+        if self._ws is None or self._ws.device != dev or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        return self._ws
+
     # ---- device pieces (each = one C-ABI call) ----
     def _K_seq(self, X, X2=None, row_blocks=None):
         """kernels.py:208-237 on RAW (unscaled) sequences (N, L, d); returns level stack (M+1, N, N2).
@@ -191,20 +199,23 @@ class SignatureKernel:
         n2, L2 = (n1, L1) if X2 is None else (X2.shape[0], X2.shape[1])
         blocks = [(0, n1)] if row_blocks is None else list(row_blocks)
         nrows = sum(e - b for b, e in blocks)
-        alloc = torch.empty if row_blocks is None else torch.zeros
-        out = alloc((self.num_levels + 1, nrows, n2), device=dev, dtype=torch.float32)
+        out = torch.empty((self.num_levels + 1, nrows, n2), device=dev, dtype=torch.float32)
         ws = self._workspace(dev, n1, L1, n2, L2, d)
         inv_ls = self._inv_ls(dev)
         keep, pptr = self._params_ptr()
-        mirror = int(X2 is None and row_blocks is None)
-        row0 = 0
         with torch.cuda.device(dev):
-            for b, e in blocks:
+            if row_blocks is None:
                 rc = lib.gpsig_seq_kern_levels(_KIND[self._kind], pptr, X.data_ptr(), n1, L1, _ptr(X2), n2, L2, d, _ptr(inv_ls),
-                                               self.num_levels, self.order, int(self.difference), b, e, out.data_ptr(), row0,
-                                               nrows, mirror, ws.data_ptr(), ws.numel(), _stream())
+                                               self.num_levels, self.order, int(self.difference), 0, n1, out.data_ptr(), 0,
+                                               nrows, int(X2 is None), ws.data_ptr(), ws.numel(), _stream())
                 _lib.check(rc, "gpsig_seq_kern_levels")
-                row0 += e - b
+            else:
+                import ctypes
+                flat = (ctypes.c_int * (2 * len(blocks)))(*[int(v) for be in blocks for v in be])
+                rc = lib.gpsig_seq_kern_levels_blocks(_KIND[self._kind], pptr, X.data_ptr(), n1, L1, _ptr(X2), n2, L2, d,
+                                                      _ptr(inv_ls), self.num_levels, self.order, int(self.difference), flat,
+                                                      len(blocks), out.data_ptr(), nrows, ws.data_ptr(), ws.numel(), _stream())
+                _lib.check(rc, "gpsig_seq_kern_levels_blocks")
         return out
 
     def _K_seq_wide(self, X, X2=None, row_blocks=None):
@@ -245,7 +256,7 @@ class SignatureKernel:
         if d > _MAX_FUSED_FEATURES:
             return self._K_seq_diag_wide(X)
         out = torch.empty((self.num_levels + 1, n), device=dev, dtype=torch.float32)
-        ws = self._workspace(dev, min(n, 64), L, min(n, 64), L, d)
+        ws = self._workspace_diag(dev, n, L, d)
         inv_ls = self._inv_ls(dev)
         keep, pptr = self._params_ptr()
         with torch.cuda.device(dev):
@@ -256,8 +267,9 @@ class SignatureKernel:
         return out
 
     def _finish(self, levels, diag1=None, diag2=None, symmetric=False, normalize=True, return_levels=False, diag_cols=None,
-                unit_weights=False):
-        """kernels.py:430-433 / :455-469 / :471-476 in one launch."""
+                unit_weights=False, out=None):
+        """kernels.py:430-433 / :455-469 / :471-476 in one launch.  `out`: preallocated (contiguous) result of the summed
+        matrix (the all-gather input of parallel.sharded_K_symm)."""
         lib = _lib.load()
         dev = levels.device
         nl = levels.shape[0]
@@ -265,7 +277,10 @@ class SignatureKernel:
         n2 = levels.shape[2] if levels.dim() == 3 else 1
         w = torch.ones(nl, device=dev, dtype=torch.float32) if unit_weights else self._weights(dev)
         lev_out = torch.empty_like(levels) if return_levels else None
-        out = None if return_levels else torch.empty(levels.shape[1:], device=dev, dtype=torch.float32)
+        if out is None or return_levels:
+            out = None if return_levels else torch.empty(levels.shape[1:], device=dev, dtype=torch.float32)
+        else:
+            assert out.is_contiguous() and tuple(out.shape) == tuple(levels.shape[1:]) and out.dtype == torch.float32
         sym = bool(symmetric and normalize)
         with torch.cuda.device(dev):
             rc = lib.gpsig_normalize_weight_sum(levels.data_ptr(), nl, n1, n2, _ptr(diag1) if normalize else 0,

@@ -44,38 +44,67 @@ def rows_of(blocks):
     return np.concatenate([np.arange(b, e, dtype=np.int64) for b, e in blocks])
 
 
-def gather_rows(local_rows, n, parts, group=None):
-    """All-gather row shards (rank r holds the rows rows_of(parts[r]), shape (len, n2)) into the full (n, n2) matrix.
+_INDEX_CACHE = {}
 
-    ONE collective: shards are padded to a common row count and exchanged with all_gather_into_tensor (NCCL); the gloo
-    backend used by the CPU tests goes through all_gather on a list."""
-    world_size = len(parts)
-    counts = [sum(e - b for b, e in p) for p in parts]
-    maxr = max(counts)
-    dev, dt, n2 = local_rows.device, local_rows.dtype, local_rows.shape[1]
-    padded = torch.zeros((maxr, n2), device=dev, dtype=dt)
-    padded[:local_rows.shape[0]] = local_rows
+
+def _shard_index(n, parts, rank, dev):
+    """Index tensors of a partition (cached per device): rows of `rank`, their int32 copy (diagonal columns), and for
+    every global row its position in the flattened (world * maxr) all-gather result."""
+    key = (n, tuple(tuple(p) for p in parts), rank, str(dev))
+    hit = _INDEX_CACHE.get(key)
+    if hit is None:
+        counts = [sum(e - b for b, e in p) for p in parts]
+        maxr = max(counts) if counts else 0
+        src = np.zeros((n,), dtype=np.int64)
+        for r, p in enumerate(parts):
+            rr = rows_of(p)
+            src[rr] = r * maxr + np.arange(len(rr))
+        rows = rows_of(parts[rank])
+        hit = (rows, torch.as_tensor(rows, device=dev), torch.as_tensor(rows.astype(np.int32), device=dev),
+               torch.as_tensor(src, device=dev), torch.as_tensor(src.astype(np.int32), device=dev), maxr)
+        if len(_INDEX_CACHE) > 64:
+            _INDEX_CACHE.clear()
+        _INDEX_CACHE[key] = hit
+    return hit
+
+
+def _all_gather_padded(padded, world_size, group):
+    """ONE collective on equally sized shards: all_gather_into_tensor (NCCL); the gloo backend used by the CPU tests (or
+    two ranks sharing one GPU) stages through host memory."""
     if world_size == 1:
-        gathered = padded[None]
-    elif dist.get_backend(group) == "nccl":
-        gathered = torch.empty((world_size, maxr, n2), device=dev, dtype=dt)
+        return padded[None]
+    if dist.get_backend(group) == "nccl":
+        gathered = torch.empty((world_size,) + tuple(padded.shape), device=padded.device, dtype=padded.dtype)
         dist.all_gather_into_tensor(gathered, padded, group=group)
-    else:  # gloo (CPU tests, or two ranks sharing one GPU): stage through host memory
-        host = padded.cpu()
-        chunks = [torch.empty_like(host) for _ in range(world_size)]
-        dist.all_gather(chunks, host, group=group)
-        gathered = torch.stack(chunks).to(dev)
-    out = torch.empty((n, n2), device=dev, dtype=dt)
-    for r, p in enumerate(parts):
-        row0 = 0
-        for b, e in p:
-            out[b:e] = gathered[r, row0:row0 + (e - b)]
-            row0 += e - b
-    return out
+        return gathered
+    host = padded.cpu()
+    chunks = [torch.empty_like(host) for _ in range(world_size)]
+    dist.all_gather(chunks, host, group=group)
+    return torch.stack(chunks).to(padded.device)
+
+
+def gather_rows(local_rows, n, parts, group=None):
+    """All-gather row shards (rank r holds the rows rows_of(parts[r]), shape (len, n2)) into the full (n, n2) matrix:
+    one collective on shards padded to a common row count, one gather kernel that puts the rows in order."""
+    world_size = len(parts)
+    rank = dist.get_rank(group) if (dist.is_initialized() and world_size > 1) else 0
+    dev, dt, n2 = local_rows.device, local_rows.dtype, local_rows.shape[1]
+    _, _, _, src, _, maxr = _shard_index(n, parts, rank, dev)
+    if local_rows.shape[0] == maxr:
+        padded = local_rows.contiguous()
+    else:
+        padded = torch.zeros((maxr, n2), device=dev, dtype=dt)
+        padded[:local_rows.shape[0]] = local_rows
+    gathered = _all_gather_padded(padded, world_size, group)
+    return gathered.reshape(world_size * maxr, n2).index_select(0, src)
 
 
 def sharded_K_symm(kern, X, group=None, blocks_per_rank=8, gather=True):
     """K(X, X) (kernels.py:400-476, X2 is None) with the pair batch sharded over the process group.
+
+    Per rank: ONE fused launch over its list of row blocks (entries j >= i only), one launch for the level diagonals of
+    all sequences, one normalise / weight / sum launch that writes straight into the all-gather input, ONE all-gather,
+    and one kernel that orders the gathered rows and fills the lower triangle from the transpose.
 
     Returns the full (N, N) matrix on every rank; gather=False returns (local rows (len, N) with only j >= i valid,
     row indices) without communicating."""
@@ -86,27 +115,28 @@ def sharded_K_symm(kern, X, group=None, blocks_per_rank=8, gather=True):
     n = Xs.shape[0]
     parts = partition(n, ws, blocks_per_rank)
     mine = parts[rk]
-    rows = rows_of(mine)
     dev = Xs.device
+    rows, ridx, cols, _, src32, maxr = _shard_index(n, parts, rk, dev)
+    padded = torch.empty((maxr, n), device=dev, dtype=torch.float32)
+    if len(rows) < maxr:
+        padded[len(rows):].zero_()
     if len(rows):
         lv = kern._K_seq(Xs, row_blocks=mine)                                   # (M+1, len(rows), N), j >= i only
         if kern.normalization:
             dg = kern._K_seq_diag(Xs)                                           # (M+1, N)
-            ridx = torch.as_tensor(rows, device=dev)
-            d1 = dg.index_select(1, ridx).contiguous()
-            cols = ridx.to(torch.int32).contiguous()
-            local = kern._finish(lv, d1, dg, normalize=True, diag_cols=cols)
+            d1 = dg.index_select(1, ridx)
+            kern._finish(lv, d1, dg, normalize=True, diag_cols=cols, out=padded[:len(rows)])
         else:
-            local = kern._finish(lv, normalize=False)
-    else:
-        local = torch.zeros((0, n), device=dev, dtype=torch.float32)
+            kern._finish(lv, normalize=False, out=padded[:len(rows)])
     if not gather:
-        return local, rows
-    K = gather_rows(local, n, parts, group)
+        return padded[:len(rows)], rows
+    gathered = _all_gather_padded(padded, ws, group)
+    K = torch.empty((n, n), device=dev, dtype=torch.float32)
     lib = _lib.load()
     with torch.cuda.device(dev):
-        rc = lib.gpsig_mirror_upper(K.data_ptr(), 1, n, torch.cuda.current_stream().cuda_stream)
-    _lib.check(rc, "gpsig_mirror_upper")
+        rc = lib.gpsig_assemble_symmetric(gathered.data_ptr(), src32.data_ptr(), n, K.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "gpsig_assemble_symmetric")
     return K
 
 

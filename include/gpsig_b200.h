@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define GPSIG_B200_VERSION 100 /* 0.1.0 */
+#define GPSIG_B200_VERSION 200 /* 0.2.0 */
 
 enum {
     GPSIG_OK = 0,
@@ -71,6 +71,11 @@ enum {
     GPSIG_PROF_NUM_CLASSES = 7
 };
 long long gpsig_launch_count(void);
+/* Tuning / experiment knobs.  Their defaults come from the environment ONCE, at first use (GPSIG_WARPFUSED,
+ * GPSIG_WARPFUSED_WARPS, GPSIG_STREAM_NCW / _R / _S, GPSIG_TENS_TC); afterwards only this call changes them
+ * (names: "warpfused", "warpfused_warps", "stream_ncw", "stream_r", "stream_s", "tens_tc").  Not thread safe against
+ * concurrent launches. */
+int gpsig_set_knob(const char* name, int value);
 int gpsig_profile_enable(int on);
 int gpsig_profile_reset(void);
 int gpsig_profile_read(int cls, double* total_ms, long long* launches, double* units);
@@ -123,8 +128,22 @@ int gpsig_seq_kern_levels(int kind, const float* params, const float* X, int n1,
                           int L2, int d, const float* inv_lengthscales, int num_levels, int order, int difference,
                           int row_begin, int row_end, float* out_levels, long out_row0, long out_rows_total, int mirror,
                           void* workspace, size_t workspace_bytes, void* stream);
+/* The same for a LIST of row blocks (a GPU's shard of the symmetric problem; no reference counterpart):
+ *     row_blocks = host array {begin_0, end_0, begin_1, end_1, ...} of global row ranges; out_levels is the compact stack
+ *     (num_levels+1, out_rows_total = sum of block sizes, n2) holding block after block.  One launch covers all blocks
+ *     where the fused kernel applies.  Symmetric (X2 == NULL): only entries j >= i of every row are written. */
+int gpsig_seq_kern_levels_blocks(int kind, const float* params, const float* X, int n1, int L1, const float* X2, int n2,
+                                 int L2, int d, const float* inv_lengthscales, int num_levels, int order, int difference,
+                                 const int* row_blocks, int num_blocks, float* out_levels, long out_rows_total,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+/* workspace of gpsig_seq_kern_diag_levels for n sequences (the prepared points of ALL n sequences live in it) */
+size_t gpsig_seq_kern_diag_workspace_bytes(int n, int L, int d, size_t budget_bytes);
 /* levels[m][i][j] = levels[m][j][i] for i > j, levels (nl, n, n) */
 int gpsig_mirror_upper(float* levels, int nl, int n, void* stream);
+/* Multi-GPU assembly of a symmetric matrix from gathered row shards (no reference counterpart):
+ *     K[i][j] = rows[row_src[i]][j] for j >= i, rows[row_src[j]][i] for j < i;  rows (*, n) holds every global row i at
+ *     position row_src[i] (n ints, device) with only its entries j >= i valid; K (n, n). */
+int gpsig_assemble_symmetric(const float* rows, const int* row_src, int n, float* K, void* stream);
 int gpsig_seq_kern_diag_levels(int kind, const float* params, const float* X, int n, int L, int d,
                                const float* inv_lengthscales, int num_levels, int order, int difference,
                                float* out_levels, void* workspace, size_t workspace_bytes, void* stream);

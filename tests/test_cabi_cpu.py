@@ -32,7 +32,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     # the ctypes prototype table covers exactly the header
     assert sorted(_lib.EXPORTED_SYMBOLS) == declared
     lib.gpsig_version.restype = ctypes.c_int
-    assert lib.gpsig_version() == 100
+    assert lib.gpsig_version() == _lib.ABI_VERSION
     lib.gpsig_error_string.restype = ctypes.c_char_p
     assert lib.gpsig_error_string(-1) == b"invalid argument"
 

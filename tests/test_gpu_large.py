@@ -166,22 +166,22 @@ def test_kuf_fast_and_generic_paths_vs_oracle(kind, L, d, M, diff):
         assert_levels_close(got, ko.K_tens_vs_seq(Z, X, increments=inc, return_levels=True), msg="Kuf %s inc=%s" % (kind, inc))
 
 
-@pytest.mark.parametrize("path", ["GPSIG_WARPFUSED", "GPSIG_FUSED"])
 @pytest.mark.parametrize("kind", ["linear", "rbf"])
-def test_fused_kernels_are_bit_identical_to_the_pipeline(kind, path, monkeypatch):
-    """The fused Gram + recursion kernels (warpfused.cu: default for Linear; fused.cu: opt-in) against the two-kernel
-    path (increment-Gram producer -> stream recursion): same arithmetic per entry, so the same bits."""
+def test_fused_kernel_against_the_pipeline(kind):
+    """The warp-fused Gram + recursion kernel (warpfused.cu, default) against the two-kernel path (increment-Gram producer
+    -> stream recursion).  Linear: same arithmetic per entry, so the same bits.  RBF: the fused kernel evaluates the
+    squared distance in the anchored form, the producer directly from the differences -- equal to fp32 rounding."""
     import ctypes
     from gpsig_b200 import _lib
     X = random_walks(75, 64, 5, 31).reshape(75, -1)
     Y = random_walks(22, 64, 5, 32).reshape(22, -1)
     k, _ = _pair(kind, 64, 5, 4, lengthscales=1.4)
-    monkeypatch.setenv("GPSIG_WARPFUSED", "0")
-    monkeypatch.delenv("GPSIG_FUSED", raising=False)
-    ref_s, ref_r = k.K(X, return_levels=True).clone(), k.K(X, Y, return_levels=True).clone()
-    monkeypatch.setenv("GPSIG_WARPFUSED", "1" if path == "GPSIG_WARPFUSED" else "0")
-    monkeypatch.setenv("GPSIG_FUSED", "1" if path == "GPSIG_FUSED" else "0")
     lib = _lib.load()
+    _lib.set_knob("warpfused", 0)
+    try:
+        ref_s, ref_r = k.K(X, return_levels=True).clone(), k.K(X, Y, return_levels=True).clone()
+    finally:
+        _lib.set_knob("warpfused", 1)
     lib.gpsig_profile_reset(); lib.gpsig_profile_enable(1)
     got_s, got_r = k.K(X, return_levels=True), k.K(X, Y, return_levels=True)
     torch.cuda.synchronize()
@@ -189,8 +189,13 @@ def test_fused_kernels_are_bit_identical_to_the_pipeline(kind, path, monkeypatch
     ms, n, un = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
     lib.gpsig_profile_read(6, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(un))
     lib.gpsig_profile_reset()
-    assert n.value == 2, "the fused kernel did not run"
-    assert torch.equal(got_s, ref_s) and torch.equal(got_r, ref_r)
+    assert n.value >= 2, "the fused kernel did not run"
+    if kind == "linear":
+        assert torch.equal(got_s, ref_s) and torch.equal(got_r, ref_r)
+    else:
+        for got, ref in ((got_s, ref_s), (got_r, ref_r)):
+            for m in range(got.shape[0]):
+                assert float((got[m] - ref[m]).abs().max()) <= 5e-6 * float(ref[m].abs().max()), m
 
 
 @pytest.mark.parametrize("kind", ["linear", "rbf"])

@@ -7,7 +7,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from gpsig_b200 import kernels, signature_algs as S  # noqa: E402
+from gpsig_b200 import kernels, _lib, signature_algs as S  # noqa: E402
 
 rng = np.random.default_rng(0)
 n, L, d, M = 10, 64, 4, 3
@@ -16,8 +16,8 @@ Y = (np.cumsum(rng.standard_normal((5, L, d)), axis=1) / np.sqrt(L)).reshape(5, 
 Z = 0.4 * rng.standard_normal((M * (M + 1) // 2, 6, 2, d))
 for cls in (kernels.SignatureLinear, kernels.SignatureRBF):
     k = cls(L * d, d, M, lengthscales=1.3)
-    for env in ("1", "0"):
-        os.environ["GPSIG_WARPFUSED"] = env
+    for knob in (1, 0):
+        _lib.set_knob("warpfused", knob)
         a, b = k.K(X), k.K(X, Y)
         torch.cuda.synchronize()
     c = k.K_tens_vs_seq(Z, X, increments=True)
