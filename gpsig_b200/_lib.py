@@ -57,6 +57,11 @@ _PROTOTYPES = {
     "gpsig_tens_seq_kern_levels": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, _c_float_p, ctypes.c_long, ctypes.c_int,
                                                   _c_float_p, ctypes.c_long, ctypes.c_int, ctypes.c_int, _c_float_p,
                                                   ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, ctypes.c_void_p]),
+    "gpsig_sigkern_levels_vjp": (ctypes.c_int, [_c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_long,
+                                                ctypes.c_long, ctypes.c_long, ctypes.c_int, _c_float_p, _c_float_p,
+                                                ctypes.c_void_p]),
+    "gpsig_tens_vs_seq_levels_vjp": (ctypes.c_int, [_c_float_p, ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_int,
+                                                    _c_float_p, _c_float_p, ctypes.c_void_p]),
     "gpsig_lr_hadamard_csc": (ctypes.c_int, [_c_float_p, ctypes.c_long, ctypes.c_int, _c_float_p, ctypes.c_int, ctypes.c_void_p,
                                              ctypes.c_void_p, ctypes.c_void_p, _c_float_p, ctypes.c_int, ctypes.c_float,
                                              _c_float_p, ctypes.c_void_p]),

@@ -134,8 +134,12 @@ constexpr int kWfMaxRowBlocks = 32;
 // 1.5e-7 |u|^2 relative to k)
 constexpr float kWfJumpThreshold = 4.0f;
 bool warpfused_supported(bool rbf, int d, int nlev, int ncols, int rowsA);
-int launch_wf_jump_flag(const float* B, long long n, int rows, int D, unsigned* flag, bool reset, cudaStream_t st);
-int launch_sigkern_warpfused(bool rbf, const float* A, const float* B, const unsigned* flag, int rowsA, int rowsB, int D,
+struct WfAnchored { float* Bu; float* Bnu; float* Banc; int nstrip; };  // column side of the anchored RBF form
+size_t wf_anchor_bytes(long long n, int rows, int D);
+int launch_wf_anchor_prep(const float* B, long long n, int rows, int D, void* buf, unsigned* flag, WfAnchored* out,
+                          cudaStream_t st);
+int launch_sigkern_warpfused(bool rbf, const float* A, const float* B, const WfAnchored* anch, const unsigned* flag, int rowsA,
+                             int rowsB, int D,
                              int npts, int n2, int nlev, int upper_only, int diag, int nblk, const int* blk_begin,
                              const int* blk_end, const long long* blk_out_row, long long ldo, long long lvl_stride, float* out,
                              cudaStream_t st);

@@ -111,7 +111,7 @@ struct SeqPlan {
     int out_rows, ncols;    // increment tile size
     int LP, P, G;
     bool fast;              // stream-fed recursion eligible (P = 16 LP <= 512 columns)
-    size_t bytesA, bytesB, bytesAn, bytesBn, fixed;
+    size_t bytesA, bytesB, bytesAn, bytesBn, bytesAnch, fixed;
 };
 
 static int make_plan(int kind, int L1, int L2, int d, int n1, int n2, bool symmetric, int difference, SeqPlan& pl) {
@@ -144,7 +144,8 @@ static int make_plan(int kind, int L1, int L2, int d, int n1, int n2, bool symme
     pl.bytesAn = align_up((size_t)n1 * pl.rowsA * 4, 256);
     pl.bytesB = symmetric ? 0 : align_up((size_t)n2 * pl.rowsB * pl.DP * 4, 256);
     pl.bytesBn = symmetric ? 0 : align_up((size_t)n2 * pl.rowsB * 4, 256);
-    pl.fixed = 256 /* jump flag */ + pl.bytesA + pl.bytesAn + pl.bytesB + pl.bytesBn + 1024;
+    pl.bytesAnch = pl.prep_mode == 3 ? wf_anchor_bytes(symmetric ? n1 : n2, pl.rowsB, pl.DP) : 0;  // anchored column side
+    pl.fixed = 256 /* jump flag */ + pl.bytesA + pl.bytesAn + pl.bytesB + pl.bytesBn + pl.bytesAnch + 1024;
     return GPSIG_OK;
 }
 
@@ -157,6 +158,7 @@ extern "C" size_t gpsig_seq_kern_workspace_bytes(int n1, int L1, int n2, int L2,
     SeqPlan pl;
     // worst case over kinds/difference: points (L rows) -- a few MB, the chunk buffer dominates
     if (make_plan(GPSIG_KERN_RBF, L1, L2, d, n1, n2, false, 0, pl) != GPSIG_OK) return 0;
+    pl.fixed += wf_anchor_bytes(n1 > n2 ? n1 : n2, L1 > L2 ? L1 : L2, pl.DP);
     size_t row_bytes = (size_t)pl.out_rows * n2 * pl.P * 4;  // one row block of i
     size_t all = row_bytes * (size_t)n1;
     if (pl.fast) {  // stream layout: whole streams of skewed rows
@@ -211,6 +213,7 @@ static int seq_kern_levels_impl(int kind, const float* params, const float* X, i
     float* An = (float*)w; w += pl.bytesAn;
     float* B = A; float* Bn = An;
     if (!symmetric) { B = (float*)w; w += pl.bytesB; Bn = (float*)w; w += pl.bytesBn; }
+    void* anch_buf = w; w += pl.bytesAnch;
     w = (uint8_t*)align_up((size_t)w, 1024);
     float* chunk = (float*)w;
     const size_t chunk_bytes = workspace_bytes - (size_t)(w - (uint8_t*)workspace);
@@ -234,11 +237,13 @@ static int seq_kern_levels_impl(int kind, const float* params, const float* X, i
     // warp-fused path: every warp computes and consumes its own increment rows (no chunk buffer, no HBM intermediate);
     // ONE launch for all row blocks
     if (use_stream && pl.fast_prod && nblk <= kWfMaxRowBlocks && warpfused_supported(rbf, d, num_levels, pl.ncols, pl.rowsA)) {
+        WfAnchored anch{};
         if (rbf) {
-            rc = launch_wf_jump_flag(B, n2, pl.rowsB, pl.DP, flag, true, st);
+            rc = launch_wf_anchor_prep(B, n2, pl.rowsB, pl.DP, anch_buf, flag, &anch, st);
             if (rc) return rc;
         }
-        rc = launch_sigkern_warpfused(rbf, A, B, rbf ? flag : nullptr, pl.rowsA, pl.rowsB, pl.DP, rbf ? pl.ncols + 1 : pl.ncols,
+        rc = launch_sigkern_warpfused(rbf, A, B, rbf ? &anch : nullptr, rbf ? flag : nullptr, pl.rowsA, pl.rowsB, pl.DP,
+                                      rbf ? pl.ncols + 1 : pl.ncols,
                                       n2, num_levels, upper ? 1 : 0, 0, nblk, blk_begin, blk_end, blk_out_row, n2, per_level,
                                       out_levels, st);
         if (rc != GPSIG_E_UNSUPPORTED) return rc ? rc : do_mirror();
@@ -311,6 +316,7 @@ extern "C" size_t gpsig_seq_kern_diag_workspace_bytes(int n, int L, int d, size_
     if (n < 1 || L < 1 || d < 1) return 0;
     SeqPlan pl;
     if (make_plan(GPSIG_KERN_RBF, L, L, d, n, n, true, 0, pl) != GPSIG_OK) return 0;
+    pl.fixed += wf_anchor_bytes(n, L, pl.DP);
     size_t one = (size_t)pl.out_rows * pl.P * 4 * (size_t)pl.G, all = (size_t)pl.out_rows * pl.P * 4 * (size_t)n;
     if (pl.fast) {
         one = stream_bytes_worst(1, pl.out_rows, pl.LP);
@@ -370,6 +376,7 @@ extern "C" int gpsig_seq_kern_diag_levels(int kind, const float* params, const f
     unsigned* flag = (unsigned*)w; w += 256;
     float* A = (float*)w; w += pl.bytesA;
     float* An = (float*)w; w += pl.bytesAn;
+    void* anch_buf = w; w += pl.bytesAnch;
     w = (uint8_t*)align_up((size_t)w, 1024);
     float* chunk = (float*)w;
     if (workspace_bytes < (size_t)(w - (uint8_t*)workspace))
@@ -379,12 +386,14 @@ extern "C" int gpsig_seq_kern_diag_levels(int kind, const float* params, const f
     const bool rbf = kind == GPSIG_KERN_RBF;
     // warp-fused path (diag mode: pairs (e, e)): no chunk buffer
     if (use_stream && pl.fast_prod && warpfused_supported(rbf, d, num_levels, pl.ncols, pl.rowsA)) {
+        WfAnchored anch{};
         rc = launch_prep_points(X, n, L, d, inv_lengthscales, pl.prep_mode, pl.DP, A, An, st);
-        if (!rc && rbf) rc = launch_wf_jump_flag(A, n, pl.rowsA, pl.DP, flag, true, st);
+        if (!rc && rbf) rc = launch_wf_anchor_prep(A, n, pl.rowsA, pl.DP, anch_buf, flag, &anch, st);
         if (rc) return rc;
         const int b0 = 0, e0 = 1;
         const long long o0 = 0;
-        rc = launch_sigkern_warpfused(rbf, A, A, rbf ? flag : nullptr, pl.rowsA, pl.rowsA, pl.DP, rbf ? pl.ncols + 1 : pl.ncols, n,
+        rc = launch_sigkern_warpfused(rbf, A, A, rbf ? &anch : nullptr, rbf ? flag : nullptr, pl.rowsA, pl.rowsA, pl.DP,
+                                      rbf ? pl.ncols + 1 : pl.ncols, n,
                                       num_levels, 0, 1, 1, &b0, &e0, &o0, n, n, out_levels, st);
         if (rc != GPSIG_E_UNSUPPORTED) return rc;
     }

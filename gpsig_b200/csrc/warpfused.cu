@@ -40,6 +40,10 @@ constexpr int kWfAnchor = 3;  // strip-local anchor point (RBF mode 1)
 struct WfParams {
     const float* A;   // prepared row-side data    (rows i, rowsA, D)
     const float* B;   // prepared column-side data (rows j, rowsB, D)
+    const float* Bu;  // RBF anchored form of the column side: 2 (y_t - a(strip of t))      (rows j, rowsB, D)
+    const float* Bnu; //                                         -|y_t - a|^2               (rows j, rowsB)
+    const float* Banc;//                                         -a per strip               (rows j, nstrip, D)
+    int nstrip;
     const unsigned* flag;  // RBF: float bits of max |u|^2 over the column side (NULL = never jumpy)
     int rowsA, rowsB;      // rowsA == steps per item (RBF: row 0 only primes the differencing)
     int LP, log2LP, G;
@@ -55,6 +59,7 @@ struct WfParams {
     float* out;
     long long out_level_stride;
     int xfloats, yfloats;  // per-warp tile sizes (floats): x tile (one buffer), y tile
+    int nufloats, ancfloats;  // RBF anchored: -|u|^2 tile (G * rowsB rounded up to 4) and anchor tile (G * LP * D)
 };
 
 __device__ __forceinline__ float wf_ex2(float x) {
@@ -129,8 +134,10 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_warpfused_kernel(const W
     const long long total = nloc * Lrow;
     if (total == 0) return;
     const long long nsteps = total + LP - 1;
-    float* xt = wsm + (size_t)warp * (2 * p.xfloats + p.yfloats);  // x tile, two buffers (diag: G sequences each)
+    float* xt = wsm + (size_t)warp * (2 * p.xfloats + p.yfloats + p.nufloats + p.ancfloats);  // x tile, two buffers
     float* yt = xt + 2 * p.xfloats;                                 // y tile of the item strip 0 entered last
+    float* nut = yt + p.yfloats;                                    // its -|u|^2 values and anchors (RBF anchored form)
+    float* anct = nut + p.nufloats;
     const int l = lane & (LP - 1), q = lane >> p.log2LP;
     const int t0 = l * W;
     const int xq = p.diag ? q * Lrow * D : 0;  // diag: pair q reads its own row sequence
@@ -201,14 +208,21 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_warpfused_kernel(const W
                     dstx[g * perx + row * C4 + pc] = __ldg(srcx + e);
                 }
             }
-            if (!p.diag) {
+            if (!p.diag || MODE == 1) {  // column side (diag, modes 0 / 2: the points are taken from the x tile)
                 float4* dsty = reinterpret_cast<float4*>(yt);
                 const int per = p.rowsB * C4;
+                const float* ysrc = MODE == 1 ? p.Bu : p.B;
                 for (int g = 0; g < p.G; ++g) {
                     int jl = jg0 + g;
                     if (jl > p.n2 - 1) jl = p.n2 - 1;  // padding pair of a ragged last group
-                    const float4* srcy = reinterpret_cast<const float4*>(p.B + (long long)jl * p.rowsB * D);
+                    const float4* srcy = reinterpret_cast<const float4*>(ysrc + (long long)jl * p.rowsB * D);
                     for (int e = lane; e < per; e += 32) dsty[g * per + e] = __ldg(srcy + e);
+                    if (MODE == 1) {
+                        for (int e = lane; e < p.rowsB; e += 32) nut[g * p.rowsB + e] = __ldg(p.Bnu + (long long)jl * p.rowsB + e);
+                        const float4* srca = reinterpret_cast<const float4*>(p.Banc + (long long)jl * p.nstrip * D);
+                        float4* dsta = reinterpret_cast<float4*>(anct) + g * LP * C4;
+                        for (int e = lane; e < p.nstrip * C4; e += 32) dsta[e] = __ldg(srca + e);
+                    }
                 }
             }
             __syncwarp();
@@ -221,58 +235,59 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_warpfused_kernel(const W
         // ---- this strip enters the item: its column points move from the tile into registers ----
         if (EV && valid && s == 0) {
             if (MODE == 1) {
-                int ta = t0 + kWfAnchor;
-                if (ta > p.rowsB - 1) ta = p.rowsB - 1;
-                if (p.diag) {
-                    const float4* src = reinterpret_cast<const float4*>(xt + par * p.xfloats + xq) + ta * C4;
-                    const int sw = (C4 == 2) ? ((ta >> 2) & 1) : 0;
+                // everything was put into the anchored form once per call (wf_anchor_prep_kernel): plain copies
+                const float4* sa = reinterpret_cast<const float4*>(anct) + (q * LP + l) * C4;
+#pragma unroll
+                for (int c = 0; c < C4; ++c) {
+                    const float4 v = sa[c];
+                    nanc[2 * c] = make_float2(v.x, v.y);
+                    nanc[2 * c + 1] = make_float2(v.z, v.w);
+                }
+#pragma unroll
+                for (int u = 0; u < W; ++u) {
+                    const int t = t0 + u;
+                    const int tc = t < p.rowsB ? t : p.rowsB - 1;  // clamp: equal points difference to exactly zero
+                    const float4* src = reinterpret_cast<const float4*>(yt + ((size_t)q * p.rowsB + tc) * D);
 #pragma unroll
                     for (int c = 0; c < C4; ++c) {
-                        const float4 v = src[c ^ sw];
-                        nanc[2 * c] = make_float2(-v.x, -v.y);
-                        nanc[2 * c + 1] = make_float2(-v.z, -v.w);
+                        const float4 v = src[c];
+                        y[u][2 * c] = make_float2(v.x, v.y);
+                        y[u][2 * c + 1] = make_float2(v.z, v.w);
                     }
-                } else {
-                    const float2* src = reinterpret_cast<const float2*>(yt + ((size_t)q * p.rowsB + ta) * D);
-#pragma unroll
-                    for (int h = 0; h < H; ++h) nanc[h] = make_float2(-src[h].x, -src[h].y);
+                    nu[u] = nut[q * p.rowsB + tc];
                 }
-            }
+            } else {
 #pragma unroll
-            for (int u = 0; u < W; ++u) {
-                const int t = t0 + u;
-                const bool ok = RBF || t < p.rowsB;          // LINEAR: increments past the end are zero
-                const int tc = t < p.rowsB ? t : p.rowsB - 1;  // RBF: clamp (equal points difference to exactly zero)
-                float2 raw[H];
-                if (p.diag) {
-                    const float4* src = reinterpret_cast<const float4*>(xt + par * p.xfloats + xq) + tc * C4;
-                    const int sw = (C4 == 2) ? ((tc >> 2) & 1) : 0;
+                for (int u = 0; u < W; ++u) {
+                    const int t = t0 + u;
+                    const bool ok = RBF || t < p.rowsB;          // LINEAR: increments past the end are zero
+                    const int tc = t < p.rowsB ? t : p.rowsB - 1;  // RBF: clamp (equal points difference to exactly zero)
+                    float2 raw[H];
+                    if (p.diag) {
+                        const float4* src = reinterpret_cast<const float4*>(xt + par * p.xfloats + xq) + tc * C4;
+                        const int sw = (C4 == 2) ? ((tc >> 2) & 1) : 0;
 #pragma unroll
-                    for (int c = 0; c < C4; ++c) {
-                        const float4 v = src[c ^ sw];
-                        raw[2 * c] = make_float2(v.x, v.y);
-                        raw[2 * c + 1] = make_float2(v.z, v.w);
+                        for (int c = 0; c < C4; ++c) {
+                            const float4 v = src[c ^ sw];
+                            raw[2 * c] = make_float2(v.x, v.y);
+                            raw[2 * c + 1] = make_float2(v.z, v.w);
+                        }
+                    } else {
+                        const float4* src = reinterpret_cast<const float4*>(yt + ((size_t)q * p.rowsB + tc) * D);
+#pragma unroll
+                        for (int c = 0; c < C4; ++c) {
+                            const float4 v = src[c];
+                            raw[2 * c] = make_float2(v.x, v.y);
+                            raw[2 * c + 1] = make_float2(v.z, v.w);
+                        }
                     }
-                } else {
-                    const float2* src = reinterpret_cast<const float2*>(yt + ((size_t)q * p.rowsB + tc) * D);
+                    if (MODE == 2) {
 #pragma unroll
-                    for (int h = 0; h < H; ++h) raw[h] = src[h];
-                }
-                if (MODE == 1) {
-                    float2 acc = make_float2(0.f, 0.f);
+                        for (int h = 0; h < H; ++h) y[u][h] = make_float2(-raw[h].x, -raw[h].y);
+                    } else {
 #pragma unroll
-                    for (int h = 0; h < H; ++h) {
-                        const float2 df = make_float2(raw[h].x + nanc[h].x, raw[h].y + nanc[h].y);
-                        acc = __ffma2_rn(df, df, acc);
-                        y[u][h] = make_float2(df.x + df.x, df.y + df.y);
+                        for (int h = 0; h < H; ++h) y[u][h] = ok ? raw[h] : make_float2(0.f, 0.f);
                     }
-                    nu[u] = -(acc.x + acc.y);
-                } else if (MODE == 2) {
-#pragma unroll
-                    for (int h = 0; h < H; ++h) y[u][h] = make_float2(-raw[h].x, -raw[h].y);
-                } else {
-#pragma unroll
-                    for (int h = 0; h < H; ++h) y[u][h] = ok ? raw[h] : make_float2(0.f, 0.f);
                 }
             }
 #pragma unroll
@@ -421,35 +436,60 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_warpfused_kernel(const W
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// the jump flag: max over the column side of |y_t - a(strip of t)|^2 in the scaled units of prep mode 3
+// column side of the anchored RBF form, once per call: for every point y_t (scaled as in prep mode 3) of every column
+// sequence, with a = the anchor of its strip (point 8 (t / 8) + 3, clamped to the last point):
+//     Bu = 2 (y_t - a),   Bnu = -|y_t - a|^2,   Banc[strip] = -a;   flag = max |y_t - a|^2 over the call (float bits)
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void wf_jump_flag_kernel(const float* __restrict__ B, long long n, int rows, int D, unsigned* __restrict__ flag) {
+__global__ void wf_anchor_prep_kernel(const float* __restrict__ B, long long n, int rows, int D, int nstrip,
+                                      float* __restrict__ Bu, float* __restrict__ Bnu, float* __restrict__ Banc,
+                                      unsigned* __restrict__ flag) {
     const long long total = n * rows;
     float worst = 0.f;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const long long seq = idx / rows;
         const int t = (int)(idx - seq * rows);
-        int ta = (t / kWfCols) * kWfCols + kWfAnchor;
+        const int strip = t / kWfCols;
+        int ta = strip * kWfCols + kWfAnchor;
         if (ta > rows - 1) ta = rows - 1;
         const float* yp = B + idx * D;
         const float* ap = B + (seq * rows + ta) * D;
         float acc = 0.f;
-        for (int c = 0; c < D; ++c) { const float df = yp[c] - ap[c]; acc = fmaf(df, df, acc); }
+        for (int c = 0; c < D; ++c) {
+            const float df = yp[c] - ap[c];
+            acc = fmaf(df, df, acc);
+            Bu[idx * D + c] = df + df;
+            if (t == ta || (t == strip * kWfCols && ta < t)) Banc[(seq * nstrip + strip) * D + c] = -ap[c];
+        }
+        Bnu[idx] = -acc;
         worst = fmaxf(worst, acc);
     }
     for (int o = 16; o > 0; o >>= 1) worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, o));
     if ((threadIdx.x & 31) == 0 && worst > 0.f) atomicMax(flag, __float_as_uint(worst));  // non-negative floats order as uints
 }
 
-int launch_wf_jump_flag(const float* B, long long n, int rows, int D, unsigned* flag, bool reset, cudaStream_t st) {
-    if (reset) {
-        cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(unsigned), st);
-        if (e != cudaSuccess) return (int)e;
-    }
+size_t wf_anchor_bytes(long long n, int rows, int D) {
+    const int nstrip = (rows + kWfCols - 1) / kWfCols;
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    return up((size_t)n * rows * D * 4) + up((size_t)n * rows * 4) + up((size_t)n * nstrip * D * 4);
+}
+
+// fills the three arrays (carved out of `buf`, wf_anchor_bytes() bytes) and the flag word
+int launch_wf_anchor_prep(const float* B, long long n, int rows, int D, void* buf, unsigned* flag, WfAnchored* out,
+                          cudaStream_t st) {
+    const int nstrip = (rows + kWfCols - 1) / kWfCols;
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    uint8_t* w = (uint8_t*)buf;
+    out->Bu = (float*)w; w += up((size_t)n * rows * D * 4);
+    out->Bnu = (float*)w; w += up((size_t)n * rows * 4);
+    out->Banc = (float*)w;
+    out->nstrip = nstrip;
+    cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(unsigned), st);
+    if (e != cudaSuccess) return (int)e;
     const long long total = n * rows;
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)num_sms() * 8;
-    wf_jump_flag_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(B, n, rows, D, flag);
+    wf_anchor_prep_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(B, n, rows, D, nstrip, out->Bu, out->Bnu, out->Banc,
+                                                                               flag);
     return check_launch();
 }
 
@@ -481,7 +521,7 @@ bool warpfused_supported(bool rbf, int d, int nlev, int ncols, int rowsA) {
 template <int MODE, int NLEV, int D, int MAXW>
 static int launch_wf_maxw(WfParams& p, cudaStream_t st) {
     auto kern = sigkern_warpfused_kernel<MODE, NLEV, D, MAXW>;
-    const size_t per_warp = (size_t)(2 * p.xfloats + p.yfloats) * sizeof(float);
+    const size_t per_warp = (size_t)(2 * p.xfloats + p.yfloats + p.nufloats + p.ancfloats) * sizeof(float);
     int nw = MAXW;
     if (env_knobs().warpfused_warps > 0 && env_knobs().warpfused_warps < nw) nw = env_knobs().warpfused_warps;
     while (nw > 1 && per_warp * nw > 232448) --nw;
@@ -513,7 +553,8 @@ static int launch_wf_lev(int nlev, WfParams& p, cudaStream_t st) {
 // from prepared data (gram.cu prep modes 1 / 3).  `npts` = strip points per pair (RBF: ncols + 1, LINEAR: ncols).
 // out[m * lvl_stride + (blk_out_row[k] + i - blk_begin[k]) * ldo + j].  diag != 0: pairs (e, e), out[m * lvl_stride + e].
 // Returns GPSIG_E_UNSUPPORTED when there is no instantiation.
-int launch_sigkern_warpfused(bool rbf, const float* A, const float* B, const unsigned* flag, int rowsA, int rowsB, int D,
+int launch_sigkern_warpfused(bool rbf, const float* A, const float* B, const WfAnchored* anch, const unsigned* flag, int rowsA,
+                             int rowsB, int D,
                              int npts, int n2, int nlev, int upper_only, int diag, int nblk, const int* blk_begin,
                              const int* blk_end, const long long* blk_out_row, long long ldo, long long lvl_stride, float* out,
                              cudaStream_t st) {
@@ -521,7 +562,10 @@ int launch_sigkern_warpfused(bool rbf, const float* A, const float* B, const uns
         return fail(GPSIG_E_BADARG, "sigkern_warpfused: bad sizes");
     if (nblk > kWfMaxRowBlocks) return fail(GPSIG_E_UNSUPPORTED, "at most %d row blocks per launch", kWfMaxRowBlocks);
     WfParams p;
+    if (rbf && !anch) return fail(GPSIG_E_BADARG, "sigkern_warpfused: the RBF form needs the anchored column side");
     p.A = A; p.B = B; p.flag = flag; p.rowsA = rowsA; p.rowsB = rowsB;
+    p.Bu = rbf ? anch->Bu : nullptr; p.Bnu = rbf ? anch->Bnu : nullptr; p.Banc = rbf ? anch->Banc : nullptr;
+    p.nstrip = rbf ? anch->nstrip : 0;
     p.LP = wf_lanes_per_pair(npts); p.log2LP = wf_log2(p.LP); p.G = 32 / p.LP;
     p.n2 = n2; p.upper_only = upper_only ? 1 : 0; p.diag = diag ? 1 : 0;
     p.NJG = (n2 + p.G - 1) / p.G;
@@ -540,14 +584,25 @@ int launch_sigkern_warpfused(bool rbf, const float* A, const float* B, const uns
     p.nitems = items;
     p.ldo = ldo; p.out = out; p.out_level_stride = lvl_stride;
     p.xfloats = (diag ? p.G : 1) * rowsA * D;
-    p.yfloats = diag ? 0 : p.G * rowsB * D;
     if (p.nitems < 1) return GPSIG_OK;
     ProfScope prof(GPSIG_PROF_FUSED, st, (double)p.nitems * p.G);
     int rc = GPSIG_E_UNSUPPORTED;
     if (rbf) {
-        if (D == 4) { rc = launch_wf_lev<1, 4>(nlev, p, st); if (!rc && flag) rc = launch_wf_lev<2, 4>(nlev, p, st); }
-        if (D == 8) { rc = launch_wf_lev<1, 8>(nlev, p, st); if (!rc && flag) rc = launch_wf_lev<2, 8>(nlev, p, st); }
+        // anchored instantiation: y tile + -|u|^2 tile + anchor tile;  direct instantiation: plain y tile (diag: none)
+        p.yfloats = p.G * rowsB * D;
+        p.nufloats = (p.G * rowsB + 3) / 4 * 4;
+        p.ancfloats = p.G * p.LP * D;
+        if (D == 4) rc = launch_wf_lev<1, 4>(nlev, p, st);
+        if (D == 8) rc = launch_wf_lev<1, 8>(nlev, p, st);
+        if (!rc && flag) {
+            p.yfloats = diag ? 0 : p.G * rowsB * D;
+            p.nufloats = p.ancfloats = 0;
+            if (D == 4) rc = launch_wf_lev<2, 4>(nlev, p, st);
+            if (D == 8) rc = launch_wf_lev<2, 8>(nlev, p, st);
+        }
     } else {
+        p.yfloats = diag ? 0 : p.G * rowsB * D;
+        p.nufloats = p.ancfloats = 0;
         if (D == 4) rc = launch_wf_lev<0, 4>(nlev, p, st);
         if (D == 8) rc = launch_wf_lev<0, 8>(nlev, p, st);
     }

@@ -47,12 +47,14 @@ class InducingSequences(SignatureInducing):
         self.len_inducing = Z.shape[1]
 
 
-def _W(feat, dev):
-    return torch.as_tensor(np.asarray(feat.W, dtype=np.float32)).to(dev)
+def _W(feat, dev, dtype=torch.float32):
+    if isinstance(feat.W, torch.Tensor):
+        return feat.W.to(device=dev, dtype=dtype)
+    return torch.as_tensor(np.asarray(feat.W, dtype=np.float64)).to(device=dev, dtype=dtype)
 
 
-def _eye(n, dev):
-    return torch.eye(n, device=dev, dtype=torch.float32)
+def _eye(n, dev, dtype=torch.float32):
+    return torch.eye(n, device=dev, dtype=dtype)
 
 
 def _check(feat, kern):
@@ -69,19 +71,19 @@ def Kuu_Kuf_Kff(feat, kern, X_new, *, jitter=0.0, full_f_cov=False):
     seq = isinstance(feat, InducingSequences)
     lv = bool(feat.learn_weights)
     if seq:
-        Z = feat.Z.reshape(len(feat), -1) if not isinstance(feat.Z, torch.Tensor) else feat.Z.reshape(len(feat), -1)
+        Z = feat.Z.reshape(len(feat), -1)
         Kzz, Kzx, Kxx = kern.K_seq_n_seq_covs(Z, X_new, full_X2_cov=full_f_cov, return_levels=lv)
     else:
         Kzz, Kzx, Kxx = kern.K_tens_n_seq_covs(feat.Z, X_new, full_X_cov=full_f_cov, return_levels=lv,
                                                increments=feat.increments)
     if lv:
-        W = _W(feat, Kzz.device)
+        W = _W(feat, Kzz.device, Kzz.dtype)
         Kzz = Kzz[0] + torch.sum(torch.matmul(torch.matmul(W, Kzz[1:]), W.transpose(-1, -2)), dim=0)
         Kzx = Kzx[0] + torch.sum(torch.matmul(W, Kzx[1:]), dim=0)
         Kxx = torch.sum(Kxx, dim=0)
-    Kzz = Kzz + jitter * _eye(len(feat), Kzz.device)
+    Kzz = Kzz + jitter * _eye(len(feat), Kzz.device, Kzz.dtype)
     if full_f_cov:
-        Kxx = Kxx + jitter * _eye(Kxx.shape[-1], Kxx.device)
+        Kxx = Kxx + jitter * _eye(Kxx.shape[-1], Kxx.device, Kxx.dtype)
     else:
         Kxx = Kxx + jitter
     return Kzz, Kzx, Kxx
@@ -97,7 +99,7 @@ def Kuf(feat, kern, X_new):
     else:
         Kzx = kern.K_tens_vs_seq(feat.Z, X_new, return_levels=lv, increments=feat.increments)
     if lv:
-        Kzx = Kzx[0] + torch.sum(torch.matmul(_W(feat, Kzx.device), Kzx[1:]), dim=0)
+        Kzx = Kzx[0] + torch.sum(torch.matmul(_W(feat, Kzx.device, Kzx.dtype), Kzx[1:]), dim=0)
     return Kzx
 
 
@@ -111,6 +113,6 @@ def Kuu(feat, kern, *, jitter=0.0, full_f_cov=False):
     else:
         Kzz = kern.K_tens(feat.Z, return_levels=lv, increments=feat.increments)
     if lv:
-        W = _W(feat, Kzz.device)
+        W = _W(feat, Kzz.device, Kzz.dtype)
         Kzz = Kzz[0] + torch.sum(torch.matmul(torch.matmul(W, Kzz[1:]), W.transpose(-1, -2)), dim=0)
-    return Kzz + jitter * _eye(len(feat), Kzz.device)
+    return Kzz + jitter * _eye(len(feat), Kzz.device, Kzz.dtype)

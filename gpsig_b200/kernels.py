@@ -11,6 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib, settings
+from . import autodiff as _ad
 from . import low_rank_calculations as _lr
 from . import signature_algs as _algs
 
@@ -67,6 +68,7 @@ class SignatureKernel:
         self.device = torch.device(device) if device is not None else None
         self._ws = None
         self.lr_rng = np.random.default_rng()   # source of the low-rank mode's draws (reseed for reproducibility)
+        self._raw = {}                           # trainable parameters in unconstrained space (set_trainable)
 
     # ---- validators (kernels.py:94-133) ----
     def _validate_number_of_features(self, input_dim, num_features):
@@ -139,14 +141,101 @@ class SignatureKernel:
             X = out
         return X
 
-    def _inv_ls(self, dev):
-        """per-feature multiplier of the (lagged) state space: gamma[p] / lengthscales[c]  (kernels.py:357-361)."""
-        if self.lengthscales is None and self.num_lags == 0:
+    def _inv_ls(self, dev, tensors=False):
+        """per-feature multiplier of the (lagged) state space: gamma[p] / lengthscales[c]  (kernels.py:357-361).  Inducing
+        tensors (`tensors`) are only touched when there are lengthscales -- the lag weights included (kernels.py:374-379,
+        :391-395), unlike sequences, which always get the lag weights (:360-361)."""
+        if self.lengthscales is None and (self.num_lags == 0 or tensors):
             return None
         inv = np.ones(self.num_features) if self.lengthscales is None else 1.0 / np.asarray(self.lengthscales, dtype=np.float64)
         if self.num_lags > 0:
             inv = (np.asarray(self.gamma, dtype=np.float64)[:, None] * inv[None, :]).reshape(-1)
         return torch.as_tensor(inv.astype(np.float32)).to(dev)
+
+    # ---- trainable parameters (the reference: gpflow Parameters with transforms.positive, kernels.py:65-66, :86) ----
+    _POSITIVE = ("variances", "sigma", "lengthscales")
+
+    def set_trainable(self, names=("variances", "sigma", "lengthscales"), device=None):
+        """Turn the named parameters into torch leaf tensors in UNCONSTRAINED space (softplus transform like gpflow's
+        transforms.positive; `lags` uses the logistic transform onto (0, 0.5) of kernels.py:80).  From then on every
+        covariance method called with autograd enabled goes through the differentiable route (autodiff.py)."""
+        dev = torch.device(device) if device is not None else self._dev()
+        for nm in names:
+            if nm == "lengthscales" and self.lengthscales is None:
+                continue
+            if nm in ("lags", "gamma") and self.num_lags == 0:
+                continue
+            val = np.asarray(getattr(self, nm), dtype=np.float64)
+            if nm == "lags":
+                raw = np.log(val / 0.5) - np.log1p(-val / 0.5)
+            elif nm in self._POSITIVE or nm == "gamma":
+                raw = _ad.inv_softplus(val)
+            else:
+                raw = val
+            self._raw[nm] = torch.tensor(raw, dtype=torch.float64, device=dev, requires_grad=True)
+        return self
+
+    def parameters(self):
+        return list(self._raw.values())
+
+    def _tparam(self, nm, dev):
+        """constrained value of a parameter as a float64 tensor on `dev` (a function of the raw leaf when trainable)"""
+        attr = {"gamma_poly": "gamma_poly"}.get(nm, nm)
+        if attr in self._raw:
+            raw = self._raw[attr].to(dev)
+            if attr == "lags":
+                return 0.5 * torch.sigmoid(raw)
+            return _ad.softplus(raw) if (attr in self._POSITIVE or attr == "gamma") else raw
+        return torch.as_tensor(np.asarray(getattr(self, attr), dtype=np.float64), device=dev)
+
+    def sync_trainable(self):
+        """copy the current constrained values of the trainable parameters into the plain (numpy) attributes the
+        non-differentiable fast path reads"""
+        for nm in self._raw:
+            with torch.no_grad():
+                v = self._tparam(nm, self._raw[nm].device).cpu().numpy()
+            setattr(self, nm, float(v) if v.ndim == 0 else v)
+
+    def _grad_mode(self, *inputs):
+        if not torch.is_grad_enabled():
+            return False
+        return bool(self._raw) or any(isinstance(t, torch.Tensor) and t.requires_grad for t in inputs)
+
+    def _check_grad_supported(self):
+        if self.order != 1:
+            raise NotImplementedError("the differentiable route covers the first-order recursions (order == 1)")
+        if self.low_rank:
+            raise NotImplementedError("the differentiable route covers the exact mode (low_rank == False)")
+
+    def _inv_ls_tensor(self, dev, tensors=False):
+        if self.lengthscales is None and (self.num_lags == 0 or tensors):
+            return None
+        inv = torch.ones(self.num_features, device=dev, dtype=torch.float64) if self.lengthscales is None \
+            else 1.0 / self._tparam("lengthscales", dev).reshape(-1)
+        if self.num_lags > 0:
+            inv = (self._tparam("gamma", dev)[:, None] * inv[None, :]).reshape(-1)
+        return inv
+
+    def _weights_tensor(self, dev):
+        return self._tparam("sigma", dev) * self._tparam("variances", dev)                       # kernels.py:471
+
+    def _to_dev64(self, X, like=None):
+        """inputs of the differentiable route: float64 on the device (numpy is never rounded to fp32 first)"""
+        dev = self._dev(X if like is None else like)
+        if isinstance(X, torch.Tensor):
+            return X.to(device=dev, dtype=torch.float64)
+        return torch.as_tensor(np.ascontiguousarray(X, dtype=np.float64)).to(dev)
+
+    def _seqs_t(self, X, presliced=False):
+        """differentiable _seqs: slice, reshape, lagged copies (tensor algebra)"""
+        X = self._to_dev64(X)
+        if not presliced:
+            X = self._slice(X)
+        X = X.reshape(X.shape[0], -1, self.num_features)
+        return _ad.add_lags(self, X)
+
+    def _tens_t(self, Z, like=None):
+        return self._to_dev64(Z, like=like)
 
     def _weights(self, dev):
         w = float(self.sigma) * np.asarray(self.variances, dtype=np.float64)                    # kernels.py:471
@@ -290,11 +379,11 @@ class SignatureKernel:
         _lib.check(rc, "gpsig_normalize_weight_sum")
         return lev_out if return_levels else out
 
-    def _scale_tens(self, Z):
-        """kernels.py:366-398 (no lags): Z / lengthscales on the last axis."""
+    def _scale_tens(self, Z, tensors=False):
+        """kernels.py:366-398 (inducing tensors: `tensors`) / :357-361 (sequences): Z x gamma / lengthscales on the last axis."""
         lib = _lib.load()
         Z = self._to_dev(Z).contiguous()
-        inv_ls = self._inv_ls(Z.device)
+        inv_ls = self._inv_ls(Z.device, tensors)
         if inv_ls is None:
             return Z
         out = torch.empty_like(Z)
@@ -341,6 +430,10 @@ class SignatureKernel:
         n, L, d = X.shape
         out = torch.empty((self.num_levels + 1, nz, n), device=X.device, dtype=torch.float32)
         inv_ls = self._inv_ls(X.device)
+        if self.lengthscales is None and self.num_lags > 0:
+            # the reference leaves the tensors alone without lengthscales but still weights the lagged copies of the
+            # sequences (kernels.py:360-361 vs :374): scale X here, nothing inside the kernel
+            X, inv_ls = self._scale_tens(X), None
         keep, pptr = self._params_ptr()
         with torch.cuda.device(X.device):
             rc = lib.gpsig_tens_seq_kern_levels(_KIND[self._kind], pptr, Z.data_ptr(), nz, int(bool(increments)), X.data_ptr(),
@@ -393,6 +486,18 @@ class SignatureKernel:
         self._check_supported()
         if presliced:
             presliced_X = presliced_X2 = True
+        if self._grad_mode(X, X2):
+            self._check_grad_supported()
+            Xt = self._seqs_t(X, presliced_X)
+            if X2 is None:
+                lv = _ad.K_seq_levels(self, Xt)
+                return _ad.finish(self, lv, symmetric=True, normalize=self.normalization, return_levels=return_levels)
+            X2t = self._seqs_t(X2, presliced_X2)
+            lv = _ad.K_seq_levels(self, Xt, X2t)
+            d1 = d2 = None
+            if self.normalization:
+                d1, d2 = _ad.K_seq_diag_levels(self, Xt), _ad.K_seq_diag_levels(self, X2t)
+            return _ad.finish(self, lv, d1, d2, normalize=self.normalization, return_levels=return_levels)
         Xs = self._seqs(X, presliced_X)
         if X2 is None:
             if self.low_rank:                                                                    # kernels.py:424-426
@@ -419,12 +524,19 @@ class SignatureKernel:
         """kernels.py:478-510."""
         self._check_supported()
         n = X.shape[0]
+        if self.normalization and self._grad_mode():
+            w = self._weights_tensor(self._dev(X)).to(torch.float32)
+            return w[:, None].expand(-1, n) if return_levels else w.sum().expand(n)
         if self.normalization:
             dev = self._dev(X)
             w = self._weights(dev)
             if return_levels:
                 return w[:, None].expand(-1, n).contiguous()
             return torch.full((n,), float(self.sigma * np.sum(self.variances)), device=dev, dtype=torch.float32)
+        if self._grad_mode(X):
+            self._check_grad_supported()
+            lv = _ad.K_seq_diag_levels(self, self._seqs_t(X, presliced))
+            return _ad.finish(self, lv[:, :, None], normalize=False, return_levels=return_levels).squeeze(-1)
         Xs = self._seqs(X, presliced)
         if self.low_rank:                                                                        # kernels.py:499-501
             lv = self._lr_diag(self._K_seq_lr_feat(self._scale_tens(Xs)))
@@ -435,19 +547,29 @@ class SignatureKernel:
     def K_tens(self, Z, return_levels=False, increments=False):
         """kernels.py:512-536."""
         self._check_supported()
+        if self._grad_mode(Z):
+            self._check_grad_supported()
+            lv = _ad.K_tens_levels(self, self._tens_t(Z), increments)
+            return _ad.finish(self, lv, normalize=False, return_levels=return_levels)
         if self.low_rank:                                                                        # kernels.py:525-527
-            Phi = self._K_tens_lr_feat(self._scale_tens(Z), increments)
+            Phi = self._K_tens_lr_feat(self._scale_tens(Z, tensors=True), increments)
             lv = self._lr_gram(Phi, Phi)
         else:
-            lv = self._K_tens(self._scale_tens(Z), increments)
+            lv = self._K_tens(self._scale_tens(Z, tensors=True), increments)
         return self._finish(lv, normalize=False, return_levels=return_levels)
 
     def K_tens_vs_seq(self, Z, X, return_levels=False, increments=False, presliced=False):
         """kernels.py:538-588."""
         self._check_supported()
+        if self._grad_mode(Z, X):
+            self._check_grad_supported()
+            Xt = self._seqs_t(X, presliced)
+            lv = _ad.K_tens_vs_seq_levels(self, self._tens_t(Z, Xt), Xt, increments)
+            d2 = _ad.K_seq_diag_levels(self, Xt) if self.normalization else None
+            return _ad.finish(self, lv, None, d2, normalize=self.normalization, return_levels=return_levels)
         Xs = self._seqs(X, presliced)
         if self.low_rank:                                                                        # kernels.py:560-568, :573-574
-            Zc, Xc = self._scale_tens(Z), self._scale_tens(Xs)
+            Zc, Xc = self._scale_tens(Z, tensors=True), self._scale_tens(Xs)
             seeds, nys = self._lr_seeds(), self._lr_samples(Zc, Xc)
             PhiZ, PhiX = self._K_tens_lr_feat(Zc, increments, nys, seeds), self._K_seq_lr_feat(Xc, nys, seeds)
             lv = self._lr_gram(PhiZ, PhiX)
@@ -460,16 +582,36 @@ class SignatureKernel:
     def K_tens_n_seq_covs(self, Z, X, full_X_cov=False, return_levels=False, increments=False, presliced=False):
         """kernels.py:590-671."""
         self._check_supported()
+        if self._grad_mode(Z, X):
+            self._check_grad_supported()
+            Xt = self._seqs_t(X, presliced)
+            Zt = self._tens_t(Z, Xt)
+            Kzz = _ad.finish(self, _ad.K_tens_levels(self, Zt, increments), normalize=False, return_levels=return_levels)
+            Kzx_lv = _ad.K_tens_vs_seq_levels(self, Zt, Xt, increments)
+            if full_X_cov:
+                Kxx_lv = _ad.K_seq_levels(self, Xt)
+                dg = torch.diagonal(Kxx_lv, dim1=1, dim2=2) if self.normalization else None       # kernels.py:632-638
+                Kxx = _ad.finish(self, Kxx_lv, symmetric=True, normalize=self.normalization, return_levels=return_levels)
+                Kzx = _ad.finish(self, Kzx_lv, None, dg, normalize=self.normalization, return_levels=return_levels)
+            else:
+                dg = _ad.K_seq_diag_levels(self, Xt)
+                Kzx = _ad.finish(self, Kzx_lv, None, dg, normalize=self.normalization, return_levels=return_levels)
+                if self.normalization:                                                               # kernels.py:655-661
+                    w = self._weights_tensor(Xt.device).to(torch.float32)
+                    Kxx = w[:, None].expand(-1, Xt.shape[0]) if return_levels else w.sum().expand(Xt.shape[0])
+                else:
+                    Kxx = _ad.finish(self, dg[:, :, None], normalize=False, return_levels=return_levels).squeeze(-1)
+            return Kzz, Kzx, Kxx
         Xs = self._seqs(X, presliced)
         PhiX = None
         if self.low_rank:                                                                        # kernels.py:612-621
-            Zc, Xc = self._scale_tens(Z), self._scale_tens(Xs)
+            Zc, Xc = self._scale_tens(Z, tensors=True), self._scale_tens(Xs)
             seeds, nys = self._lr_seeds(), self._lr_samples(Zc, Xc)
             PhiZ, PhiX = self._K_tens_lr_feat(Zc, increments, nys, seeds), self._K_seq_lr_feat(Xc, nys, seeds)
             Kzz = self._finish(self._lr_gram(PhiZ, PhiZ), normalize=False, return_levels=return_levels)
             Kzx_lv = self._lr_gram(PhiZ, PhiX)
         else:
-            Kzz = self._finish(self._K_tens(self._scale_tens(Z), increments), normalize=False, return_levels=return_levels)
+            Kzz = self._finish(self._K_tens(self._scale_tens(Z, tensors=True), increments), normalize=False, return_levels=return_levels)
             Kzx_lv = self._K_tens_vs_seq(Z, Xs, increments)
         if full_X_cov:
             Kxx_lv = self._lr_gram(PhiX, PhiX) if self.low_rank else self._K_seq(Xs)
@@ -497,6 +639,29 @@ class SignatureKernel:
         the reference (Q2); the evident intent is implemented here.
         """
         self._check_supported()
+        if self._grad_mode(X, X2):
+            self._check_grad_supported()
+            Xa, Xb = self._seqs_t(X, presliced=True), self._seqs_t(X2, presliced)
+            Kxx_lv, Kxx2_lv = _ad.K_seq_levels(self, Xa), _ad.K_seq_levels(self, Xa, Xb)
+            d1 = torch.diagonal(Kxx_lv, dim1=1, dim2=2) if self.normalization else None
+            Kxx = _ad.finish(self, Kxx_lv, symmetric=True, normalize=self.normalization, return_levels=return_levels)
+            if full_X2_cov:
+                K22_lv = _ad.K_seq_levels(self, Xb)
+                d2 = torch.diagonal(K22_lv, dim1=1, dim2=2) if self.normalization else None
+                K22 = _ad.finish(self, K22_lv, symmetric=True, normalize=self.normalization, return_levels=return_levels)
+            else:
+                d2 = _ad.K_seq_diag_levels(self, Xb)
+                if self.normalization:
+                    w = self._weights_tensor(Xb.device).to(torch.float32)
+                    K22 = w[:, None].expand(-1, Xb.shape[0]) if return_levels else w.sum().expand(Xb.shape[0])
+                else:
+                    K22 = _ad.finish(self, d2[:, :, None], normalize=False, return_levels=return_levels).squeeze(-1)
+            if self.normalization and literal and not full_X2_cov:                                   # quirk Q4
+                once = _ad.finish(self, Kxx2_lv, d1, None, normalize=True, return_levels=True, unit_weights=True)
+                Kxx2 = _ad.finish(self, once, d1, d2, normalize=True, return_levels=return_levels)
+            else:
+                Kxx2 = _ad.finish(self, Kxx2_lv, d1, d2, normalize=self.normalization, return_levels=return_levels)
+            return Kxx, Kxx2, K22
         Xa = self._seqs(X, presliced=True)
         Xb = self._seqs(X2, presliced)
         Phi2 = None
@@ -590,11 +755,15 @@ class SignaturePoly(SignatureKernel):
 
     def __init__(self, input_dim, num_features, num_levels, gamma=1, degree=3, **kwargs):
         super().__init__(input_dim, num_features, num_levels, **kwargs)
-        self.gamma = float(gamma)
+        # the reference stores the offset as `self.gamma` (kernels.py:838), which overwrites the lag weights of the base
+        # class (:82) and breaks num_lags > 0; here it has its own name, `gamma` stays the lag weights
+        self.gamma_poly = float(gamma)
         self.degree = float(degree)
+        if self.num_lags == 0:
+            self.gamma = self.gamma_poly   # same attribute name as the reference when there is no clash
 
     def _static_params(self):
-        return [self.gamma, self.degree]
+        return [self.gamma_poly, self.degree]
 
 
 class SignatureRBF(SignatureKernel):

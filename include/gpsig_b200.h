@@ -68,7 +68,8 @@ enum {
     GPSIG_PROF_EPILOGUE = 4,   /* normalise / weight / sum, mirror (a7) */
     GPSIG_PROF_TENS = 5,       /* inducing-tensor kernels (a9-a11) and low-rank kernels (a15) */
     GPSIG_PROF_FUSED = 6,      /* fused increment-Gram + recursion kernel (a3 + a4 in one launch, no HBM intermediate) */
-    GPSIG_PROF_NUM_CLASSES = 7
+    GPSIG_PROF_VJP = 7,        /* reverse-mode kernels (gpsig_*_vjp) */
+    GPSIG_PROF_NUM_CLASSES = 8
 };
 long long gpsig_launch_count(void);
 /* Tuning / experiment knobs.  Their defaults come from the environment ONCE, at first use (GPSIG_WARPFUSED,
@@ -185,6 +186,23 @@ int gpsig_tens_vs_seq_levels(const float* M, int num_levels, long nz, long n, in
 int gpsig_tens_seq_kern_levels(int kind, const float* params, const float* Z, long nz, int increments, const float* X,
                                long n, int L, int d, const float* inv_lengthscales, int num_levels, int order,
                                int difference, float* out_levels, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * f1  Reverse mode of the two first-order recursions.  The reference has no counterpart in its own sources: it trains
+ *     through signature_algs.py:28-33 and :116-125 by TensorFlow autodiff (gpsig/training.py:140-203 drives it); a binding
+ *     registers these as the gradients of the ops that replace signature_kern_first_order /
+ *     signature_kern_tens_vs_seq_first_order.  Both act on the INCREMENTS, i.e. on what
+ *     signature_algs.py:26 / :114 (and kernels.py:330) produce -- the forward value is gpsig_sigkern_levels /
+ *     gpsig_tens_vs_seq_levels with difference = 0, increments = 0 on the same tensor.
+ *       gpsig_sigkern_levels_vjp:     Delta addressed like M of gpsig_sigkern_levels (n1, L1, n2, L2 = increment counts),
+ *                                     G (num_levels+1, n1, n2) = dL/d levels, Delta_bar dense (n1, L1, n2, L2) = dL/dDelta.
+ *       gpsig_tens_vs_seq_levels_vjp: H (T, nz, n, Lh) dense, G (num_levels+1, nz, n), H_bar (T, nz, n, Lh).
+ *     First order only (order == 1).  Nothing per entry is stored between the sweeps: the forward state is run backwards.
+ * ------------------------------------------------------------------------------------------------------------- */
+int gpsig_sigkern_levels_vjp(const float* Delta, int n1, int L1, int n2, int L2, long stride_i, long stride_s,
+                             long stride_j, int num_levels, const float* G, float* Delta_bar, void* stream);
+int gpsig_tens_vs_seq_levels_vjp(const float* H, int num_levels, long nz, long n, int Lh, const float* G, float* H_bar,
+                                 void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * a15  low-rank mode.  The random projection of low_rank_calculations.py:152-193 (very sparse Gaussian JL, matrix R of
