@@ -1,34 +1,45 @@
 #!/usr/bin/env python
 """
-bench.py -- sequence-pairs/sec of the full signature-kernel covariance K(X, X) (BASELINE.json's metric).
+bench.py -- throughput of the signature-kernel covariance path on BASELINE.json's configurations.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4|cfg2] [--kernel linear|rbf]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4|cfg2|cfg3|cfg5|cfg1] [--kernel linear|rbf]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference ...      # the reference's own algorithm (fp64 NumPy oracle) on the host cores
 
-A "step" is one evaluation of K(X, X) for the whole workload: point prep -> warp-fused increment-Gram + level recursion
-kernel (or, as the `pipeline` pass: chunked increment-Gram producer -> bulk-copy-staged stream recursion) -> normalise /
-weight / sum -> mirror (gpsig_b200.kernels.SignatureKernel.K; with N > 1 gpsig_b200.parallel.sharded_K_symm: row blocks
-dealt over the ranks, ONE all-gather of the assembled rows).  The problem size is fixed as N grows ("scaling": "strong").
+Workloads (a "step" is one evaluation of the workload's covariance through the public API of gpsig_b200):
+  cfg4 (default)  full K(X, X), N=4096 L=128 d=8 M=5, SignatureRBF      -- BASELINE.json configs[3], the metric's shape
+  cfg2            full K(X, X), N=1024 L=64 d=6 M=4, SignatureLinear    -- configs[1]
+  cfg1            full K(X, X), N=32 L=20 d=3 M=3, SignatureRBF          -- configs[0] (the reference's CPU-sized case)
+  cfg3            Kuf, InducingTensors Z=256 (increments) vs N=4096 L=128 d=8 M=5 -- configs[2] (--low-rank: low-rank mode)
+  cfg5            SVGP ELBO step (Kuu_Kuf_Kff + Cholesky + conditional + KL), N=8192 Z=512 L=100 d=10 M=6 -- configs[4]
+With N > 1 ranks the pair batch is sharded (gpsig_b200.parallel): K(X, X) by row blocks + ONE all-gather, Kuf by sequence
+shards + one all-gather, the ELBO data-parallel + one scalar all-reduce.  The problem size is fixed ("scaling": "strong").
 
-  value     N^2 output pairs / step time, X already resident in HBM (CUDA events, max over ranks, L2 flushed between
-            steps).
-  e2e       the same through the public API with HOST buffers: X starts in pinned host memory, K ends in pinned
-            host memory, both copies inside the timed region.
-  roofline  the dominant kernel of the step: algorithmic bytes per pair (4 L1 L2 + 4 (M+1)) x pairs processed
-            / its own CUDA-event duration (events recorded around every launch inside the library: gpsig_profile_*),
-            against MEASURED_PEAKS.json's hbm_gbs.  The default path is the warp-fused kernel (Gram + recursion in one
-            launch, no HBM intermediate: FP32-bound, the figure is the Gram bytes it stands for); `pipeline` carries the
-            same K steps through the HBM-staged two-kernel path (GPSIG_WARPFUSED=0) with the roofline of its recursion
-            kernel sigkern_fo_stream_kernel -- the kernel the HBM roofline really bounds.
+  value     work units / step time with the inputs resident in HBM (CUDA events, max over ranks, L2 flushed between
+            steps).  Units: output pairs N^2 (K(X, X)), tensor-sequence pairs Z N (Kuf, ELBO).
+  e2e       the same through the public API with HOST buffers: inputs start in pinned host memory, the result ends in
+            pinned host memory, both copies inside the timed region.  With N > 1 every rank uploads the (replicated)
+            inputs and downloads ITS slab of the result into one host buffer shared by the ranks.
+  roofline  the dominant kernel of the step, from CUDA events recorded around every launch inside the library
+            (gpsig_profile_*).  The default K(X, X) path is the warp-fused kernel (Gram + recursion in one launch, no HBM
+            intermediate), which the FP32 pipe bounds: `achieved` = algorithmic FP32 lane-operations per second (per Gram
+            entry: d + 2 dot-product / norm terms, 2 for the 2-D increment, 2M - 1 for the recursion -- RBF; d + 2M - 1
+            Linear; each FADD / FFMA / FMUL lane-op counts once) against 148 SMs x 128 lanes x the SM clock measured during
+            the run.  `hbm_equivalent` keeps the figure the north star is phrased in (Gram bytes the kernel stands for per
+            second against the measured copy bandwidth), and `pipeline` carries the same K steps through the HBM-staged
+            two-kernel path (knob warpfused = 0) with the roofline of its recursion kernel sigkern_fo_stream_kernel -- the
+            kernel the HBM roofline really bounds.  Kuf / ELBO: the tensor-vs-sequence kernel, FP32 lane-ops likewise.
   cpu_baseline  the fp64 NumPy oracle (op-for-op restatement of the reference, oracle/gpsig_oracle.py) on a bounded
-            sample (n_s x n_s pairs of the same L/d/M) over all host cores; a reported baseline, not the target.
+            sample of the same workload over all host cores; a reported baseline, not the target.
+  parity    after the timed region: entries of the result the timed steps produced against the fp64 oracle (K(X, X): a
+            12 x 12 corner AND 512 entries drawn uniformly from the whole N x N matrix; Kuf / ELBO: a sample block).
 
 Nothing here reads /root/reference.  oracle/ is executed only as the CPU baseline (cpu_baseline / --impl reference) and,
-after the timed region, as the checker of a 12 x 12 corner of the result ("parity").
+after the timed region, as the checker.
 """
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -43,12 +54,16 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 WORKLOADS = {
-    # BASELINE.json configs[3] / the north star's target shape; fits one GPU through the chunked pipeline
-    "cfg4": dict(N=4096, L=128, d=8, M=5, kernel="rbf", desc="Full K(X,X) N=4096 L=128 d=8 M=5"),
-    # BASELINE.json configs[1]
-    "cfg2": dict(N=1024, L=64, d=6, M=4, kernel="linear", desc="SignatureLinear K(X,X) N=1024 L=64 d=6 M=4"),
+    "cfg4": dict(type="ksymm", N=4096, L=128, d=8, M=5, kernel="rbf", desc="Full K(X,X) N=4096 L=128 d=8 M=5"),
+    "cfg2": dict(type="ksymm", N=1024, L=64, d=6, M=4, kernel="linear", desc="SignatureLinear K(X,X) N=1024 L=64 d=6 M=4"),
+    "cfg1": dict(type="ksymm", N=32, L=20, d=3, M=3, kernel="rbf", desc="SignatureRBF K(X,X) N=32 L=20 d=3 M=3"),
+    "cfg3": dict(type="kuf", N=4096, Z=256, L=128, d=8, M=5, kernel="rbf",
+                 desc="Kuf with InducingTensors Z=256, N=4096 L=128 d=8 M=5"),
+    "cfg5": dict(type="elbo", N=8192, Z=512, L=100, d=10, M=6, kernel="rbf",
+                 desc="SVGP ELBO step (Kuu Cholesky + Kuf matmul + KL) SignatureRBF N=8192 Z=512 L=100 d=10 M=6"),
 }
-METRIC = "sequence-pairs/sec for full K(X,X)"
+METRICS = {"ksymm": "sequence-pairs/sec for full K(X,X)", "kuf": "tensor-sequence pairs/sec for Kuf",
+           "elbo": "tensor-sequence pairs/sec through one SVGP ELBO step"}
 UNIT = "pairs/s"
 
 
@@ -58,18 +73,32 @@ def synth_X(N, L, d, seed=0):
     return (np.cumsum(rng.standard_normal((N, L, d)), axis=1) / np.sqrt(L)).reshape(N, L * d)
 
 
+def synth_Z(X, L, d, M, nz, seed=2):
+    """SURVEY.md 8d / gpsig/utils.py:25-63: pairs of consecutive observations sampled from X plus 0.4 randn."""
+    rng = np.random.default_rng(seed)
+    T = M * (M + 1) // 2
+    Xr = X.reshape(X.shape[0], L, d)
+    seq = rng.integers(0, X.shape[0], size=(T, nz))
+    t = rng.integers(0, L - 1, size=(T, nz))
+    return np.stack([Xr[seq, t], Xr[seq, t + 1]], axis=2) + 0.4 * rng.standard_normal((T, nz, 2, d))
+
+
 def lengthscales_for(kind, d):
     # RBF: sqrt(d)-scale heuristic (gpsig/utils.py:88-97 gives sqrt(E|x-x'|^2 d) ~ O(sqrt(d)) for unit-scale walks)
     return float(np.sqrt(d)) if kind == "rbf" else 1.0
 
 
+def units_per_step(wl):
+    return wl["N"] * wl["N"] if wl["type"] == "ksymm" else wl["Z"] * wl["N"]
+
+
 # ----------------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle over a process pool (one row block per task)
+# CPU arm: the oracle over a process pool
 # ----------------------------------------------------------------------------------------------------------------------
 _W = {}
 
 
-def _cpu_init(kind, L, d, M, ls, Xs):
+def _cpu_init(kind, L, d, M, ls, payload):
     try:
         from threadpoolctl import threadpool_limits
         _W["lim"] = threadpool_limits(1)
@@ -77,7 +106,7 @@ def _cpu_init(kind, L, d, M, ls, Xs):
         pass
     from oracle import gpsig_oracle as O
     _W["ko"] = O.SignatureKernelOracle(kind, L * d, d, M, lengthscales=ls)
-    _W["Xs"] = Xs
+    _W.update(payload)
 
 
 def _cpu_rows(be):
@@ -86,39 +115,72 @@ def _cpu_rows(be):
     return b, ko._K_seq(Xs[b:e], Xs)  # (M+1, e-b, n): Gram + recursion exactly as kernels.py:226 + signature_algs.py:8-35
 
 
-class CpuReference:
-    """K(X, X) of n_s sequences by the oracle, rows blocks spread over `cores` worker processes."""
+def _cpu_kuf_cols(be):
+    b, e = be
+    ko = _W["ko"]
+    return b, ko.K_tens_vs_seq(_W["Z"], _W["X"][b:e], increments=True)  # kernels.py:538-588 on a block of sequences
 
-    def __init__(self, kind, L, d, M, n_s, cores, row_block=4):
+
+class CpuReference:
+    """The workload's covariance on a bounded sample by the oracle, blocks spread over `cores` worker processes."""
+
+    def __init__(self, wl, kind, n_s, cores):
         import multiprocessing as mp
         from oracle import gpsig_oracle as O
-        self.kind, self.L, self.d, self.M, self.n_s, self.cores = kind, L, d, M, n_s, cores
+        self.wl, self.kind, self.n_s, self.cores = wl, kind, n_s, cores
+        L, d, M = wl["L"], wl["d"], wl["M"]
         self.ls = lengthscales_for(kind, d)
         self.ko = O.SignatureKernelOracle(kind, L * d, d, M, lengthscales=self.ls)
         self.X = synth_X(n_s, L, d, seed=0)
-        self.Xs = self.ko._scale_seq(self.ko._seqs(self.X))
-        self.blocks = [(b, min(n_s, b + row_block)) for b in range(0, n_s, row_block)]
-        self.pool = mp.get_context("spawn").Pool(cores, initializer=_cpu_init,
-                                                 initargs=(kind, L, d, M, self.ls, self.Xs))
+        if wl["type"] == "ksymm":
+            self.Xs = self.ko._scale_seq(self.ko._seqs(self.X))
+            self.blocks = [(b, min(n_s, b + 4)) for b in range(0, n_s, 4)]
+            payload = {"Xs": self.Xs}
+            self.units = n_s * n_s
+            self.what = "K(X,X) of %d x %d pairs" % (n_s, n_s)
+        else:
+            self.nz = min(wl["Z"], 64)
+            self.Z = synth_Z(self.X, L, d, M, self.nz)
+            step = max(1, n_s // (4 * cores))
+            self.blocks = [(b, min(n_s, b + step)) for b in range(0, n_s, step)]
+            payload = {"Z": self.Z, "X": self.X}
+            self.units = self.nz * n_s
+            self.what = "%s of %d tensors x %d sequences" % (
+                "Kuf" if wl["type"] == "kuf" else "ELBO step (Kuf blocks + dense algebra)", self.nz, n_s)
+        self.pool = mp.get_context("spawn").Pool(cores, initializer=_cpu_init, initargs=(kind, L, d, M, self.ls, payload))
 
     def step(self):
-        lv = np.empty((self.M + 1, self.n_s, self.n_s))
-        for b, part in self.pool.imap_unordered(_cpu_rows, self.blocks):
-            lv[:, b:b + part.shape[1]] = part
-        # kernels.py:430-433, :471-476
-        lv = lv + self.ko.jitter * np.eye(self.n_s)[None]
-        dsq = np.sqrt(np.diagonal(lv, axis1=-2, axis2=-1))
-        lv = lv / (dsq[:, :, None] * dsq[:, None, :])
-        return (lv * self.ko._weights()[:, None, None]).sum(axis=0)
+        from oracle import gpsig_oracle as O
+        if self.wl["type"] == "ksymm":
+            lv = np.empty((self.wl["M"] + 1, self.n_s, self.n_s))
+            for b, part in self.pool.imap_unordered(_cpu_rows, self.blocks):
+                lv[:, b:b + part.shape[1]] = part
+            # kernels.py:430-433, :471-476
+            lv = lv + self.ko.jitter * np.eye(self.n_s)[None]
+            dsq = np.sqrt(np.diagonal(lv, axis1=-2, axis2=-1))
+            lv = lv / (dsq[:, :, None] * dsq[:, None, :])
+            return (lv * self.ko._weights()[:, None, None]).sum(axis=0)
+        Kzx = np.empty((self.nz, self.n_s))
+        for b, part in self.pool.imap_unordered(_cpu_kuf_cols, self.blocks):
+            Kzx[:, b:b + part.shape[1]] = part
+        if self.wl["type"] == "kuf":
+            return Kzx
+        # ELBO (models.py:39-73): Kzz, conditional, KL, Bernoulli expectations on top of the Kuf blocks
+        Kzz = self.ko.K_tens(self.Z, increments=True) + self.ko.jitter * np.eye(self.nz)
+        Kxx = np.full((self.n_s,), float(np.sum(self.ko._weights()))) + self.ko.jitter
+        q_mu, q_sqrt = np.zeros((self.nz, 1)), np.eye(self.nz)[None]
+        fm, fv = O.base_conditional(Kzx, Kzz, Kxx, q_mu, full_cov=False, q_sqrt=q_sqrt, white=True)
+        Y = (np.arange(self.n_s)[:, None] % 2).astype(np.float64)
+        return np.array([np.sum(O.bernoulli_variational_expectations(fm, fv, Y)) - O.gauss_kl(q_mu, q_sqrt)])
 
     def close(self):
         self.pool.close()
         self.pool.join()
 
 
-def time_cpu_reference(kind, L, d, M, n_s, steps, warmup):
+def time_cpu_reference(wl, kind, n_s, steps, warmup):
     cores = os.cpu_count() or 1
-    ref = CpuReference(kind, L, d, M, n_s, cores)
+    ref = CpuReference(wl, kind, n_s, cores)
     try:
         for _ in range(warmup):
             ref.step()
@@ -129,9 +191,13 @@ def time_cpu_reference(kind, L, d, M, n_s, steps, warmup):
     finally:
         ref.close()
     assert np.isfinite(K).all()
-    return dict(value=n_s * n_s / dt, unit=UNIT, cores=cores, kind="port",
-                sample="fp64 NumPy oracle (oracle/gpsig_oracle.py), K(X,X) of %d x %d pairs at L=%d d=%d M=%d %s, %d worker "
-                       "processes, %.2f s/step" % (n_s, n_s, L, d, M, kind, cores, dt)), dt
+    return dict(value=ref.units / dt, unit=UNIT, cores=cores, kind="port",
+                sample="fp64 NumPy oracle (oracle/gpsig_oracle.py), %s at L=%d d=%d M=%d %s, %d worker processes, %.2f s/step"
+                       % (ref.what, wl["L"], wl["d"], wl["M"], kind, cores, dt)), dt
+
+
+def cpu_sample_size(args, wl):
+    return min(args.cpu_sample_n, wl["N"]) if wl["type"] == "ksymm" else min(4 * args.cpu_sample_n, wl["N"])
 
 
 def run_reference(args, wl):
@@ -139,13 +205,13 @@ def run_reference(args, wl):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     kind = args.kernel or wl["kernel"]
-    cb, dt = time_cpu_reference(kind, wl["L"], wl["d"], wl["M"], args.cpu_sample_n, max(1, args.steps), min(args.warmup, 1))
+    cb, dt = time_cpu_reference(wl, kind, cpu_sample_size(args, wl), max(1, args.steps), min(args.warmup, 1))
     line = {
-        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
+        "impl": "reference", "metric": METRICS[wl["type"]], "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["desc"], "static_kernel": kind, "N": wl["N"], "L": wl["L"], "d": wl["d"], "M": wl["M"],
-                   "sample": "%d x %d pairs per step" % (args.cpu_sample_n, args.cpu_sample_n)},
+                   "sample": cb["sample"]},
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -211,12 +277,74 @@ def load_peaks():
 
 
 def load_traffic(key):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the recursion kernel from the committed ncu capture."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu captures (profiles/traffic.json)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         return json.load(open(p)).get(key)
     except Exception:
         return None
+
+
+def fp32_ops_per_entry(kind, d, M):
+    """algorithmic FP32 lane-operations per Gram entry of the fused K(X, X) kernel (see the module docstring)"""
+    return (d + 2) + 2 + (2 * M - 1) if kind == "rbf" else d + (2 * M - 1)
+
+
+def fp32_ops_per_kuf_entry(kind, d):
+    """per (component, tensor, sequence, time step): two static-kernel evaluations (RBF: d + 2 each; Linear: one d-term dot
+    product of increments), the tensor increment, the time increment, 2 for the recursion"""
+    return 2 * (d + 2) + 1 + 1 + 2 if kind == "rbf" else d + 2
+
+
+class SharedHostMatrix:
+    """One pinned host matrix visible to every rank of the node (file in /dev/shm mapped shared, registered with CUDA):
+    each rank copies ITS slab of the result there, so the e2e path needs no second collective."""
+
+    def __init__(self, shape, rank, world, tag):
+        import torch
+        import torch.distributed as dist
+        self.path = "/dev/shm/gpsig_b200_%s_%s" % (tag, os.environ.get("MASTER_PORT", str(os.getpid())))
+        n = int(np.prod(shape))
+        if rank == 0:
+            with open(self.path, "wb") as f:
+                f.truncate(n * 4)
+        if world > 1:
+            dist.barrier()
+        self.t = torch.from_file(self.path, shared=True, size=n, dtype=torch.float32).reshape(shape)
+        self.registered = False
+        try:
+            rc = torch.cuda.cudart().cudaHostRegister(self.t.data_ptr(), n * 4, 0)
+            self.registered = (int(rc) == 0)
+        except Exception:
+            self.registered = False
+        if world > 1:
+            dist.barrier()
+        self.rank = rank
+
+    def close(self):
+        import torch
+        try:
+            if self.registered:
+                torch.cuda.cudart().cudaHostUnregister(self.t.data_ptr())
+        except Exception:
+            pass
+        if self.rank == 0:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+
+
+def read_profile(lib, _lib, classes):
+    out = {}
+    for name, c in classes:
+        ms, n, un = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
+        _lib.check(lib.gpsig_profile_read(c, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(un)), "gpsig_profile_read")
+        out[name] = (ms.value, n.value, un.value)
+    return out
+
+
+PROF_CLASSES = (("prep", 0), ("producer", 1), ("recursion", 2), ("recursion_other", 3), ("epilogue", 4), ("tens", 5), ("fused", 6))
 
 
 def run_ours(args, wl):
@@ -231,29 +359,63 @@ def run_ours(args, wl):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from gpsig_b200 import kernels, parallel, _lib, settings
+    from gpsig_b200 import kernels, parallel, models, inducing_variables as iv, _lib, settings
     lib = _lib.load()
     if args.workspace_gb:
         settings.workspace_budget_bytes = int(args.workspace_gb * (1 << 30))
 
+    wtype = wl["type"]
     N, L, d, M = wl["N"], wl["L"], wl["d"], wl["M"]
     kind = args.kernel or wl["kernel"]
     cls = dict(linear=kernels.SignatureLinear, rbf=kernels.SignatureRBF)[kind]
-    kern = cls(L * d, d, M, lengthscales=lengthscales_for(kind, d))
+    kw = dict(low_rank=True) if (args.low_rank and wtype == "kuf") else {}
+    kern = cls(L * d, d, M, lengthscales=lengthscales_for(kind, d), **kw)
     Xnp = synth_X(N, L, d, seed=0).astype(np.float32)
     Xh = torch.from_numpy(Xnp).pin_memory()
     Xd = Xh.to(dev)
-    Kh = torch.empty((N, N), dtype=torch.float32).pin_memory()
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    units = units_per_step(wl)
+    Zd = Zh = model = None
+    if wtype in ("kuf", "elbo"):
+        nz = wl["Z"]
+        Znp = synth_Z(Xnp.astype(np.float64), L, d, M, nz).astype(np.float32)
+        Zh = torch.from_numpy(Znp).pin_memory()
+        Zd = Zh.to(dev)
+    if wtype == "elbo":
+        Ynp = (np.arange(N)[:, None] % 2).astype(np.float64)
+        rngq = np.random.default_rng(7)
+        model = models.SVGP(Xd, torch.from_numpy(Ynp).to(dev), kern, models.Bernoulli(), iv.InducingTensors(Zd, M, increments=True),
+                            num_latent=1, q_mu=0.1 * rngq.standard_normal((nz, 1)))
 
-    def step_dev():
-        if world > 1:
-            return parallel.sharded_K_symm(kern, Xd, blocks_per_rank=args.blocks_per_rank)
-        return kern.K(Xd)
+    # result buffers on the host: one matrix shared by the ranks (every rank writes its slab)
+    out_shape = {"ksymm": (N, N), "kuf": (wl.get("Z", 1), N), "elbo": (1, 1)}[wtype]
+    shared = SharedHostMatrix(out_shape, rank, world, args.workload) if wtype != "elbo" else None
+    Hh = shared.t if shared is not None else torch.empty(out_shape, dtype=torch.float32).pin_memory()
+    slab = parallel.column_shards(out_shape[0] if wtype == "ksymm" else out_shape[1], world)[rank]
+
+    def step_dev(X=None, Z=None):
+        X = Xd if X is None else X
+        if wtype == "ksymm":
+            return parallel.sharded_K_symm(kern, X, blocks_per_rank=args.blocks_per_rank) if world > 1 else kern.K(X)
+        if wtype == "kuf":
+            Zz = Zd if Z is None else Z
+            if world > 1:
+                return parallel.sharded_K_tens_vs_seq(kern, Zz, X, increments=True)
+            return kern.K_tens_vs_seq(Zz, X, increments=True)
+        with torch.no_grad():
+            return parallel.sharded_elbo(model, X=X) if world > 1 else model._build_likelihood(X, model.Y)
 
     def step_e2e():
-        K = parallel.sharded_K_symm(kern, Xh, blocks_per_rank=args.blocks_per_rank) if world > 1 else kern.K(Xh)
-        Kh.copy_(K, non_blocking=True)
+        X = Xh.to(dev, non_blocking=True)
+        if wtype == "ksymm":
+            K = step_dev(X)
+            Hh[slab[0]:slab[1]].copy_(K[slab[0]:slab[1]], non_blocking=True)
+        elif wtype == "kuf":
+            K = step_dev(X, Zh.to(dev, non_blocking=True))
+            Hh[:, slab[0]:slab[1]].copy_(K[:, slab[0]:slab[1]], non_blocking=True)
+        else:
+            K = step_dev(X)
+            Hh.copy_(K.reshape(1, 1).to(torch.float32), non_blocking=True)
         return K
 
     def barrier():
@@ -280,7 +442,7 @@ def run_ours(args, wl):
         return float(t.item()), clocks
 
     for _ in range(args.warmup):
-        K = step_dev()
+        step_dev()
     barrier()
 
     lib.gpsig_profile_reset()
@@ -290,12 +452,7 @@ def run_ours(args, wl):
     ms_total, clocks = timed(step_dev, args.steps, uuid)
     l1 = lib.gpsig_launch_count()
     lib.gpsig_profile_enable(0)
-    import ctypes
-    prof = {}
-    for name, c in (("prep", 0), ("producer", 1), ("recursion", 2), ("recursion_other", 3), ("epilogue", 4), ("fused", 6)):
-        ms, n, un = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
-        _lib.check(lib.gpsig_profile_read(c, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(un)), "gpsig_profile_read")
-        prof[name] = (ms.value, n.value, un.value)
+    prof = read_profile(lib, _lib, PROF_CLASSES)
     lib.gpsig_profile_reset()
     launches = torch.tensor([l1 - l0], device=dev, dtype=torch.int64)
     if world > 1:
@@ -304,11 +461,12 @@ def run_ours(args, wl):
     # e2e: host buffers in, host buffer out
     step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)
+    barrier()
 
-    # the same steps through the two-kernel pipeline (increment-Gram producer -> HBM -> stream recursion), the design the
-    # HBM roofline describes; the default path above is the warp-fused kernel, which never writes the Gram tensor
+    # K(X, X): the same steps through the two-kernel pipeline (increment-Gram producer -> HBM -> stream recursion), the
+    # design the HBM roofline describes; the default path above is the warp-fused kernel, which never writes the Gram tensor
     prof_pipe, ms_pipe = None, None
-    if prof["fused"][0] > 0:
+    if wtype == "ksymm" and prof["fused"][0] > 0 and not args.no_pipeline:
         _lib.set_knob("warpfused", 0)
         try:
             step_dev()
@@ -316,83 +474,138 @@ def run_ours(args, wl):
             lib.gpsig_profile_enable(1)
             ms_pipe, _ = timed(step_dev, args.steps)
             lib.gpsig_profile_enable(0)
-            prof_pipe = {}
-            for name, c in (("prep", 0), ("producer", 1), ("recursion", 2), ("epilogue", 4)):
-                ms, n, un = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
-                _lib.check(lib.gpsig_profile_read(c, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(un)), "gpsig_profile_read")
-                prof_pipe[name] = (ms.value, n.value, un.value)
+            prof_pipe = read_profile(lib, _lib, (("prep", 0), ("producer", 1), ("recursion", 2), ("epilogue", 4)))
             lib.gpsig_profile_reset()
         finally:
             _lib.set_knob("warpfused", 1)
-    if rank == 0:
-        assert np.isfinite(Kh.numpy()[:8]).all()
 
+    barrier()  # every rank's slab of the last e2e step has landed in the shared host buffer
     if rank != 0:
+        if shared is not None:
+            barrier()  # rank 0 reads the shared buffer for the parity check before anyone unmaps it
+            shared.close()
         if world > 1:
             dist.destroy_process_group()
         return
     ms_step = ms_total / args.steps
-    value = N * N / (ms_step * 1e-3)
-    # roofline of the recursion kernel (rank 0's launches)
-    peak, peak_src = load_peaks()
-    b_pair = 4 * L * L + 4 * (M + 1)
-    def roof(kname, cls_prof, total_ms, traffic, note=None):
+    value = units / (ms_step * 1e-3)
+    peak_hbm, peak_src = load_peaks()
+    sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or 1965.0)
+    peak_fp32 = 148 * 128 * sm_hz / 1e12  # T lane-ops / s
+
+    def roof_hbm(kname, cls_prof, total_ms, traffic):
+        b_pair = 4 * L * L + 4 * (M + 1)
         r_ms, r_n, r_units = cls_prof
         achieved = (r_units * b_pair) / (r_ms * 1e-3) / 1e9 if r_ms > 0 else 0.0
-        out = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-               "traffic": traffic, "peak_source": peak_src, "bytes_per_pair": b_pair, "pairs_per_launch": r_units / max(r_n, 1),
-               "launches": r_n, "avg_launch_ms": r_ms / max(r_n, 1), "kernel_share_of_step": r_ms / total_ms}
-        if note:
-            out["note"] = note
-        return out
+        return {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak_hbm, "unit": "GB/s", "frac": achieved / peak_hbm,
+                "traffic": traffic, "peak_source": peak_src, "bytes_per_pair": b_pair, "pairs_per_launch": r_units / max(r_n, 1),
+                "launches": r_n, "avg_launch_ms": r_ms / max(r_n, 1), "kernel_share_of_step": r_ms / total_ms}
+
+    def roof_fp32(kname, cls_prof, total_ms, ops_per_unit, traffic, how):
+        r_ms, r_n, r_units = cls_prof
+        achieved = r_units * ops_per_unit / (r_ms * 1e-3) / 1e12 if r_ms > 0 else 0.0
+        return {"bound": "fp32", "kernel": kname, "achieved": achieved, "peak": peak_fp32, "unit": "Tlaneop/s",
+                "frac": achieved / peak_fp32, "traffic": traffic,
+                "peak_source": "148 SMs x 128 FP32 lanes x %.0f MHz (SM clock sampled under load during this run)" % (sm_hz / 1e6),
+                "lane_ops_per_unit": ops_per_unit, "unit_of_work": how, "units_per_launch": r_units / max(r_n, 1), "launches": r_n,
+                "avg_launch_ms": r_ms / max(r_n, 1), "kernel_share_of_step": r_ms / total_ms}
 
     pipeline = None
-    if prof["fused"][0] > 0:
-        # default path: Gram + recursion in ONE kernel.  `achieved` is the ALGORITHMIC Gram bytes (same per-pair figure) the
-        # kernel stands for per second; its real DRAM traffic (`traffic`) is the inputs and outputs only -- the kernel is
-        # FP32-issue bound, the HBM roofline is what it removes.  The `pipeline` object below carries the HBM-staged
-        # two-kernel path measured in this same run.
-        roofline = roof("sigkern_warpfused_kernel", prof["fused"], ms_total,
-                        load_traffic("%s_warpfused_bytes_per_launch" % args.workload) if world == 1 else None,
-                        "fused Gram + recursion: no HBM intermediate (FP32-issue bound); see `pipeline.roofline` for the "
-                        "HBM-staged recursion kernel")
-        if prof_pipe is not None:
-            pipeline = {"ms_per_step": ms_pipe / args.steps, "value": N * N / (ms_pipe / args.steps * 1e-3), "unit": UNIT,
-                        "how": "same steps with GPSIG_WARPFUSED=0: increment-Gram producer -> HBM chunk -> stream recursion",
-                        "stages": {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
-                                   for k, v in prof_pipe.items()},
-                        "roofline": roof("sigkern_fo_stream_kernel", prof_pipe["recursion"], ms_pipe,
-                                         load_traffic("%s_recursion_bytes_per_launch" % args.workload) if world == 1 else None)}
+    if wtype == "ksymm":
+        if prof["fused"][0] > 0:
+            per_pair = fp32_ops_per_entry(kind, d, M) * (L - 1) * (L - 1)
+            traffic = load_traffic("%s_warpfused_%s_bytes_per_launch" % (args.workload, kind)) if world == 1 else None
+            roofline = roof_fp32("sigkern_warpfused_kernel", prof["fused"], ms_total, per_pair, traffic,
+                                 "sequence pair = (L-1)^2 Gram entries x %d lane-ops" % fp32_ops_per_entry(kind, d, M))
+            roofline["hbm_equivalent"] = roof_hbm("sigkern_warpfused_kernel", prof["fused"], ms_total, traffic)
+            roofline["hbm_equivalent"]["note"] = ("Gram bytes the fused kernel stands for per second; it never reads them "
+                                                  "(see `pipeline.roofline` for the HBM-staged recursion kernel)")
+            if prof_pipe is not None:
+                pipeline = {"ms_per_step": ms_pipe / args.steps, "value": units / (ms_pipe / args.steps * 1e-3), "unit": UNIT,
+                            "how": "same steps with knob warpfused=0: increment-Gram producer -> HBM chunk -> stream recursion",
+                            "stages": {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
+                                       for k, v in prof_pipe.items()},
+                            "roofline": roof_hbm("sigkern_fo_stream_kernel", prof_pipe["recursion"], ms_pipe,
+                                                 load_traffic("%s_recursion_bytes_per_launch" % args.workload) if world == 1 else None)}
+        else:
+            roofline = roof_hbm("sigkern_fo_stream_kernel", prof["recursion"], ms_total,
+                                load_traffic("%s_recursion_bytes_per_launch" % args.workload) if world == 1 else None)
     else:
-        roofline = roof("sigkern_fo_stream_kernel", prof["recursion"], ms_total,
-                        load_traffic("%s_recursion_bytes_per_launch" % args.workload) if world == 1 else None)
+        T = M * (M + 1) // 2
+        per_pair = fp32_ops_per_kuf_entry(kind, d) * T * L
+        roofline = roof_fp32("tens_seq_fast_kernel", prof["tens"], ms_total, per_pair,
+                             load_traffic("%s_tens_bytes_per_launch" % args.workload) if world == 1 else None,
+                             "(tensor, sequence) pair = T L = %d x %d component-time entries x %d lane-ops"
+                             % (T, L, fp32_ops_per_kuf_entry(kind, d)))
     stages = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in prof.items()}
-    p_ms, p_n, p_units = prof["producer"]
-    if p_ms > 0:
-        stages["producer"]["store_GBps"] = p_units * 4 * (L - 1) * kernels_pitch(L) / (p_ms * 1e-3) / 1e9
 
-    # parity spot check (not timed): a corner of the matrix the timed steps produced against the fp64 oracle
+    # parity (not timed): entries of what the timed steps produced against the fp64 oracle
     from oracle import gpsig_oracle as O
-    nc = 12
     ko = O.SignatureKernelOracle(kind, L * d, d, M, lengthscales=lengthscales_for(kind, d))
-    ref = ko.K(Xnp[:nc].astype(np.float64))
-    parity = {"corner": "%dx%d" % (nc, nc), "max_abs_err_over_max_abs_ref": float(np.max(np.abs(Kh.numpy()[:nc, :nc] - ref)) / np.max(np.abs(ref))),
-              "tolerance": 1e-4}
+    X64 = Xnp.astype(np.float64)
+    if wtype == "ksymm":
+        Kn = Hh.numpy()
+        nc = min(12, N)
+        ref = ko.K(X64[:nc])
+        parity = {"corner": "%dx%d" % (nc, nc),
+                  "max_abs_err_over_max_abs_ref": float(np.max(np.abs(Kn[:nc, :nc] - ref)) / np.max(np.abs(ref))), "tolerance": 1e-4}
+        rngp = np.random.default_rng(123)
+        ns = min(512, N * N)
+        ii, jj = rngp.integers(0, N, size=ns), rngp.integers(0, N, size=ns)
+        scaled = lambda s: ko._scale_seq(ko._seqs(X64[s:s + 1]))  # noqa: E731
+        dg = {int(s): ko._K_seq_diag(scaled(s))[:, 0] for s in np.unique(np.concatenate([ii, jj]))}  # (M+1,) per sequence
+        w = ko._weights()
+        worst, big = 0.0, 0.0
+        for a, b in zip(ii, jj):
+            lv = ko._K_seq(scaled(a), scaled(b))[:, 0, 0]
+            lv = lv + (ko.jitter if a == b else 0.0)                                              # kernels.py:431
+            val = float(np.sum(w * lv / (np.sqrt(dg[int(a)] + ko.jitter) * np.sqrt(dg[int(b)] + ko.jitter))))
+            worst, big = max(worst, abs(float(Kn[a, b]) - val)), max(big, abs(val))
+        parity["random_entries"] = {"count": int(ns), "max_abs_err_over_max_abs_ref": worst / big, "tolerance": 1e-4,
+                                    "how": "entries (i, j) drawn uniformly from the N x N result of the timed e2e steps"}
+    elif wtype == "kuf" and not args.low_rank:
+        zs, ns_ = min(8, wl["Z"]), min(24, N)
+        Z64 = Zh.numpy().astype(np.float64)
+        ref = ko.K_tens_vs_seq(Z64[:, :zs], X64[:ns_], increments=True)
+        parity = {"block": "%dx%d" % (zs, ns_),
+                  "max_abs_err_over_max_abs_ref": float(np.max(np.abs(Hh.numpy()[:zs, :ns_] - ref)) / np.max(np.abs(ref))),
+                  "tolerance": 1e-4}
+    elif wtype == "elbo":
+        # the bound itself on a sub-problem small enough for the oracle
+        zs, ns_ = 16, 48
+        Z64 = Zh.numpy().astype(np.float64)[:, :zs]
+        q_mu_s = np.asarray(model.q_mu)[:zs]
+        msub = models.SVGP(Xd[:ns_], model.Y[:ns_], kern, models.Bernoulli(), iv.InducingTensors(Zd[:, :zs], M, increments=True),
+                           num_latent=1, q_mu=q_mu_s)
+        got = msub.compute_log_likelihood()
+        ref = O.svgp_elbo(ko, Z64, X64[:ns_], model.Y[:ns_].cpu().numpy(), q_mu_s, np.eye(zs)[None],
+                          likelihood="bernoulli", increments=True)[0]
+        parity = {"sub_problem": "Z=%d N=%d" % (zs, ns_), "elbo": got, "oracle_elbo": float(ref),
+                  "rel_err": abs(got - ref) / abs(ref), "tolerance": 1e-4}
+    else:
+        parity = {"note": "low-rank mode is randomised: parity is defined on injected draws (tests/test_gpu_lowrank.py)"}
+    if shared is not None and world > 1:
+        barrier()  # the other ranks may unmap the shared buffer now
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu_baseline, _ = time_cpu_reference(kind, L, d, M, args.cpu_sample_n, 1, 0)
+        cpu_baseline, _ = time_cpu_reference(wl, kind, cpu_sample_size(args, wl), 1, 0)
+    par = ({"ksymm": "row-sharded x%d + one all-gather", "kuf": "sequence-sharded x%d + one all-gather",
+            "elbo": "data-parallel x%d + one scalar all-reduce"}[wtype] % world) if world > 1 else "single GPU"
+    h2d = int(Xh.numel() * 4 + (Zh.numel() * 4 if (Zh is not None and wtype == "kuf") else 0))
+    d2h_rank = {"ksymm": (slab[1] - slab[0]) * N * 4, "kuf": out_shape[0] * (slab[1] - slab[0]) * 4, "elbo": 4}[wtype]
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRICS[wtype], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": wl["desc"], "static_kernel": kind, "N": N, "L": L, "d": d, "M": M, "order": 1,
-                   "normalization": True, "symmetric_half_computed": True,
-                   "parallelism": "row-sharded x%d + one all-gather" % world if world > 1 else "single GPU",
-                   "l2": "flushed between steps (512 MiB memset)",
+                   "normalization": True, "parallelism": par, "l2": "flushed between steps (512 MiB memset)",
                    "workspace_budget_GiB": settings.workspace_budget_bytes / (1 << 30)},
-        "e2e": {"value": N * N / (ms_e2e / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(Xh.numel() * 4),
-                "d2h_bytes_per_step": int(Kh.numel() * 4), "ms_per_step": ms_e2e / args.steps},
+        "e2e": {"value": units / (ms_e2e / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+                "d2h_bytes_per_step": int(np.prod(out_shape)) * 4, "ms_per_step": ms_e2e / args.steps,
+                "per_rank": {"h2d_bytes": h2d, "d2h_bytes": int(d2h_rank)},
+                "host_result": ("one pinned host buffer shared by the ranks; every rank writes its slab" if world > 1
+                                else "pinned host buffer")},
         "gpu_launches": int(launches.item()),
         "clocks": clocks,
         "roofline": roofline,
@@ -401,18 +614,16 @@ def run_ours(args, wl):
         "parity": parity,
         "cpu_baseline": cpu_baseline,
     }
+    if wtype == "ksymm":
+        line["config"]["symmetric_half_computed"] = True
+    else:
+        line["config"]["Z"] = wl["Z"]
+        line["config"]["low_rank"] = bool(args.low_rank)
     print(json.dumps(line), flush=True)
+    if shared is not None:
+        shared.close()
     if world > 1:
         dist.destroy_process_group()
-
-
-def kernels_pitch(L):
-    """column pitch of the increment-Gram chunk buffer (16 columns per lane, power-of-two lanes per pair)."""
-    need = max(2, -(-(L - 1) // 16))
-    lp = 1
-    while lp < need:
-        lp *= 2
-    return 16 * lp
 
 
 def main():
@@ -423,8 +634,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--kernel", default=None, choices=["linear", "rbf"])
-    ap.add_argument("--cpu-sample-n", type=int, default=128, help="CPU arm: n_s x n_s pairs per step")
+    ap.add_argument("--low-rank", action="store_true", help="cfg3: low-rank mode (kernels.py low_rank=True)")
+    ap.add_argument("--cpu-sample-n", type=int, default=128,
+                    help="CPU arm: n_s x n_s pairs (K) / 4 n_s sequences (Kuf, ELBO) per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip the second pass through the two-kernel pipeline")
     ap.add_argument("--workspace-gb", type=float, default=None)
     ap.add_argument("--blocks-per-rank", type=int, default=8)
     args = ap.parse_args()

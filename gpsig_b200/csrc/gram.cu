@@ -418,27 +418,31 @@ int launch_prep_points(const float* X, long long n, int L, int d, const float* i
 template <int KIND>
 __global__ void gram_kernel(const float* __restrict__ X, long long rows1, const float* __restrict__ X2, long long rows2,
                             int d, KernParams kp, float* __restrict__ out, long long ld) {
-    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long r = (long long)blockIdx.y * blockDim.y + threadIdx.y;
-    if (r >= rows1 || c >= rows2) return;
+    // rows on grid.x (up to 2^31 - 1 blocks of 8 rows: N L of the low-rank mode's Nystrom map runs into the millions), column
+    // tiles on grid.y with a stride loop (grid.y is capped at 65535)
+    const long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+    if (r >= rows1) return;
     const float* x = X + r * d;
-    const float* y = X2 + c * d;
-    float dot = 0.f, sq = 0.f, xx = 0.f, yy = 0.f;
-    for (int k = 0; k < d; ++k) {
-        const float a = x[k], b = y[k];
-        dot = fmaf(a, b, dot);
-        const float df = a - b;
-        sq = fmaf(df, df, sq);
-        xx = fmaf(a, a, xx);
-        yy = fmaf(b, b, yy);
+    for (long long c = (long long)blockIdx.y * blockDim.x + threadIdx.x; c < rows2; c += (long long)gridDim.y * blockDim.x) {
+        const float* y = X2 + c * d;
+        float dot = 0.f, sq = 0.f, xx = 0.f, yy = 0.f;
+        for (int k = 0; k < d; ++k) {
+            const float a = x[k], b = y[k];
+            dot = fmaf(a, b, dot);
+            const float df = a - b;
+            sq = fmaf(df, df, sq);
+            xx = fmaf(a, a, xx);
+            yy = fmaf(b, b, yy);
+        }
+        out[r * ld + c] = KIND == GPSIG_KERN_SPECTRAL ? spectral_eval(x, y, d, kp) : kern_eval<KIND>(dot, sq, xx, yy, kp);
     }
-    out[r * ld + c] = KIND == GPSIG_KERN_SPECTRAL ? spectral_eval(x, y, d, kp) : kern_eval<KIND>(dot, sq, xx, yy, kp);
 }
 
 template <int KIND>
 static int launch_gram_kind(const float* X, long long r1, const float* X2, long long r2, int d, KernParams kp, float* out,
                             long long ld, cudaStream_t st) {
-    dim3 block(32, 8), grid((unsigned)((r2 + 31) / 32), (unsigned)((r1 + 7) / 8));
+    const long long ctiles = (r2 + 31) / 32;
+    dim3 block(32, 8), grid((unsigned)((r1 + 7) / 8), (unsigned)(ctiles < 65535 ? ctiles : 65535));
     gram_kernel<KIND><<<grid, block, 0, st>>>(X, r1, X2, r2, d, kp, out, ld);
     return check_launch();
 }

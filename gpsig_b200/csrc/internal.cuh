@@ -143,6 +143,12 @@ int launch_sigkern_warpfused(bool rbf, const float* A, const float* B, const WfA
                              int npts, int n2, int nlev, int upper_only, int diag, int nblk, const int* blk_begin,
                              const int* blk_end, const long long* blk_out_row, long long ldo, long long lvl_stride, float* out,
                              cudaStream_t st);
+// tcgen05 Kuf (tens_tc.cu): split-TF32 Gram on the tensor cores; applies when the scaled data lies within kTcRadius2 of
+// its mean (decided on the device: `flag` holds the float bits of max |x - c|^2).
+constexpr float kTcRadius2 = 16.0f;
+bool tens_tc_supported(int kind, int d, int nlev, int order, int increments, int difference, int L);
+int launch_tens_seq_tc(const float* Z, long long nz, const float* X, long long n, int L, int d, const float* inv_ls, int nlev,
+                       float* out, unsigned* flag, cudaStream_t st);
 // Higher-order recursion (signature_algs.py:37-74), same addressing.
 int launch_sigkern_ho(const float* M, int n1, int Lrows, int n2, int ncols, long long si, long long ss, long long sj,
                       int nlev, int order, int difference, int upper_only, int i_off, int j_off, long long ldo,

@@ -234,6 +234,7 @@ struct TsfFastParams {
     int rowsX;        // L (points) or L - 1 (increments)
     int increments, difference;
     float* out;       // (NLEV + 1, nz, n)
+    const unsigned* tcflag;  // non-NULL: the tcgen05 kernel (tens_tc.cu) takes the call when the data is compact
 };
 
 constexpr int kTsfZPerBlock = 4;   // warps per block, one inducing tensor each
@@ -242,6 +243,7 @@ constexpr int kTsfSeqPerThread = 2;
 template <bool RBF, int NLEV, int DPA>
 __global__ void __launch_bounds__(kTsfZPerBlock * 32) tens_seq_fast_kernel(const TsfFastParams p) {
     constexpr int T = NLEV * (NLEV + 1) / 2, H = DPA / 2, NS = kTsfSeqPerThread;
+    if (p.tcflag != nullptr && __uint_as_float(*p.tcflag) <= kTcRadius2) return;  // tens_tc.cu did this call
     // per warp: [T][nst][DPA] then [T] floats; LINEAR stores dz (nst = 1); RBF with increments stores z^0 and 2 dz, and
     // -|dz|^2 in the trailing array
     extern __shared__ __align__(16) float szf[];
@@ -528,16 +530,25 @@ extern "C" int gpsig_tens_seq_kern_levels(int kind, const float* params, const f
         const int xmode = rbf ? 3 : (difference ? 1 : 0);
         const int rowsX = xmode == 1 ? L - 1 : L;
         float* fb = nullptr;
-        cudaError_t fe = cudaMallocAsync((void**)&fb, (size_t)(zpts + xpts) * DPA * sizeof(float), st);
+        cudaError_t fe = cudaMallocAsync((void**)&fb, (size_t)(zpts + xpts) * DPA * sizeof(float) + 256, st);
         if (fe != cudaSuccess) return (int)fe;
         float* Zs = fb;
         float* Xs = Zs + zpts * DPA;
-        int frc = launch_prep_points(Z, zpts, 1, d, inv_lengthscales, rbf ? 3 : 0, DPA, Zs, nullptr, st);
+        unsigned* tcflag = nullptr;
+        int frc = GPSIG_OK;
+        // tensor-core path first (returns at once on the device when the data is too spread for it), then the CUDA-core
+        // kernel, which returns at once when the tensor-core kernel did the work
+        if (tens_tc_supported(kind, d, num_levels, order, increments, difference, L)) {
+            tcflag = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(fb) + ((size_t)(zpts + xpts) * DPA * sizeof(float) + 15) / 16 * 16);
+            frc = launch_tens_seq_tc(Z, nz, X, n, L, d, inv_lengthscales, num_levels, out_levels, tcflag, st);
+        }
+        if (!frc) frc = launch_prep_points(Z, zpts, 1, d, inv_lengthscales, rbf ? 3 : 0, DPA, Zs, nullptr, st);
         if (!frc) frc = launch_prep_points(X, n, L, d, inv_lengthscales, xmode, DPA, Xs, nullptr, st);
         if (!frc) {
             TsfFastParams fp;
             fp.Z = Zs; fp.X = Xs; fp.nz = nz; fp.n = n; fp.rowsX = rowsX;
             fp.increments = increments ? 1 : 0; fp.difference = difference ? 1 : 0; fp.out = out_levels;
+            fp.tcflag = tcflag;
             frc = launch_tsf_fast(rbf, num_levels, DPA, fp, st);
         }
         cudaFreeAsync(fb, st);

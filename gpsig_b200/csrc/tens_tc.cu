@@ -1,0 +1,506 @@
+// tens_tc.cu -- Kuf (kernels.py:313-340 + signature_algs.py:101-127) for SignatureRBF with the static-kernel Gram on the
+// 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM, operands staged by TMA).
+//
+// The Gram kappa(z, x_t) of an inducing-tensor point against every time step of every sequence is > 95 % of the arithmetic
+// of Kuf and it IS a contraction (K = d): exactly what the north star keeps tensor cores for.  In scaled coordinates
+// (log2 k = -|z - x|^2) the exponent is 2<z, x> - |z|^2 - |x|^2 -- one dot product of augmented vectors.  Plain TF32
+// (10-bit mantissa) is useless for an exponent, so every factor is split into two TF32 pieces and the norms into three,
+// all laid out along K:
+//     A row (tensor point): [ 2z_hi | 2z_hi | 2z_lo | 1 1 1 | nz_1 nz_2 nz_3 ]       nz = -|z|^2
+//     B row (time step)   : [  x_hi |  x_lo |  x_hi | nx_1 nx_2 nx_3 | 1 1 1 ]       nx = -|x|^2
+// (3d + 6 K-slots, padded to a multiple of 32: one or two 128-byte swizzle atoms), accumulated in fp32 by the MMA:
+// error ~ 3 * 2^-22 * |z| |x| in the exponent.  That is small only when the data sits within a few lengthscales of
+// the centre the coordinates are taken from (the data mean): the prep kernel leaves max |x - c|^2 in a flag word, this
+// kernel returns at once when it exceeds kTcRadius2, and the CUDA-core kernel of tens.cu (anchored differences, good
+// anywhere) returns at once when it does not -- both are launched, no host synchronisation.
+//
+// One CTA per SM, persistent over work items (tile of 128 rows x chunk of sequences):
+//   * rows: the (tensor, component) pairs.  A level's components form a CHAIN (r_p[t] = h_p[t] * sum_{t'<t} r_{p-1}[t']);
+//     chains are packed into warps of 32 TMEM lanes without ever splitting one (row map built on the host), lane = row.
+//   * warp 8, one elected lane: TMA loads (A tiles once per item, B tiles of 64 time steps through a ring) and the MMAs --
+//     per tile 2 x (K/8) tcgen05.mma (M=128, N=64): D0 = exponents against the z^0 points, D1 against the z^1 points,
+//     side by side in TMEM (128 columns per buffer, 2 buffers for each of the 2 warp sets = all 512 columns).
+//   * warps 0-7: two sets of 4 (one warp per TMEM lane quarter); set s takes the sequences n = s (mod 2) of the chunk.  Per
+//     16 time steps a thread reads its row's 2 x 16 exponents (tcgen05.ld 32x32b.x16), v = 2^D1 - 2^D0, h = time
+//     increment of v, then NLEV rounds of (r = h * c_in, running exclusive prefix c, hand c to the next lane of the chain
+//     through a per-warp shared-memory patch).  The prefix carries over tiles; at the end of a sequence the last lane of
+//     each chain owns K_m(z, x_n).
+// MUFU.EX2 is the bound by design (2 per Gram entry; everything else is ~7 issue slots per entry).
+#include <vector>
+
+#include "internal.cuh"
+
+namespace gpsig {
+
+constexpr int kTcRows = 128;     // rows (TMEM lanes) per tile
+constexpr int kTcNT = 64;        // time steps per MMA tile
+constexpr int kTcNB = 16;        // time steps per epilogue block
+constexpr int kTcXPitch = 20;    // floats per lane row of the exchange patch (16 + pad: conflict-free 16-byte accesses)
+
+struct TcRow { int z, m, p, k; };  // tensor, level (0 = padding row), position in the chain, component index
+
+struct TcParams {
+    const TcRow* rows;       // (ntiles * 128)
+    const unsigned* flag;    // float bits of max |x - c|^2 (scaled)
+    int ntiles, nch, chunk;  // row tiles, sequence chunks, sequences per chunk
+    long long nz, n;
+    int Lp;                  // padded sequence length (multiple of 64)
+    float* out;              // (NLEV + 1, nz, n)
+};
+
+// ---- PTX wrappers --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float tc_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor:
+// start address >> 4 in [0, 14), LBO in [16, 30) (= 1, unused for swizzled K-major), SBO in [32, 46), version 1 in
+// [46, 48), layout type SWIZZLE_128B = 2 in [61, 64))
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr) {
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), both K-major,
+// N >> 3 in [17, 23), M >> 4 in [24, 29)
+constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcNT >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
+
+// ---- the kernel ----------------------------------------------------------------------------------------------------
+// KA = 128-byte K atoms per operand row (1: K = 32 slots, d <= 8;  2: K = 64, d <= 19);  S = stages of the B ring
+template <int NLEV, int KA, int S>
+__global__ void __launch_bounds__(288, 1)
+tens_seq_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapZ0,
+                   const __grid_constant__ CUtensorMap mapZ1, const TcParams p) {
+    if (__uint_as_float(*p.flag) > kTcRadius2) return;  // data too spread for the split-TF32 exponent: tens.cu does the call
+    extern __shared__ __align__(1024) uint8_t tsm_raw[];
+    constexpr uint32_t kABytes = KA * kTcRows * 128, kBBytes = KA * kTcNT * 128;
+    // layout: A0 | A1 | B ring | exchange patches (8 warps x 33 rows) | barriers | tmem base   (1024-byte aligned: the
+    // 128-byte swizzle of TMA and of the MMA descriptors is a function of the absolute shared-memory address)
+    uint8_t* tsm = tsm_raw + ((1024u - (smem_u32(tsm_raw) & 1023u)) & 1023u);
+    const uint32_t smem0 = smem_u32(tsm);
+    const uint32_t sA0 = smem0, sA1 = sA0 + kABytes, sB = sA1 + kABytes;
+    float* xpatch = reinterpret_cast<float*>(tsm + 2 * kABytes + S * kBBytes);
+    constexpr uint32_t kPatchBytes = 8 * 33 * kTcXPitch * 4;
+    const uint32_t bars = smem0 + 2 * kABytes + S * kBBytes + kPatchBytes;
+    const uint32_t b_full = bars, b_empty = bars + 8 * S, t_full = bars + 16 * S, t_empty = t_full + 32, a_full = t_empty + 32,
+                   mma_done = a_full + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tsm + 2 * kABytes + S * kBBytes + kPatchBytes + 16 * S + 80);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < S; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(t_full + 8 * i, 1); mbar_init(t_empty + 8 * i, 4); }
+        mbar_init(a_full, 1);
+        mbar_init(mma_done, 1);
+        fence_mbar_init();
+    }
+    if (warp == 8) {  // TMEM: all 512 columns (one CTA per SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp < 8) {  // the "ones" row of the warp's exchange patch: what the first lane of a chain multiplies by
+        float* xb = xpatch + warp * 33 * kTcXPitch;
+        if (lane < kTcNB) xb[32 * kTcXPitch + lane] = 1.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_per_seq = p.Lp / kTcNT;
+    const long long nitems = (long long)p.ntiles * p.nch;
+
+    if (warp == 8) {
+        // ===== producer: TMA + MMA issue, one lane ===================================================================
+        if (lane == 0) {
+            tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapZ0); tma_prefetch_desc(&mapZ1);
+            long long ld_idx = 0, mma_idx = 0;      // B tiles loaded / multiplied so far (ring position)
+            long long cnt[2] = {0, 0};              // tiles issued per warp set (TMEM buffer = cnt & 1)
+            int item_no = 0;
+            for (long long item = blockIdx.x; item < nitems; item += gridDim.x, ++item_no) {
+                const int zt = (int)(item / p.nch), ch = (int)(item - (long long)zt * p.nch);
+                const long long n0 = (long long)ch * p.chunk;
+                const long long n1 = n0 + p.chunk < p.n ? n0 + p.chunk : p.n;
+                const long long ntile_item = (n1 - n0) * tiles_per_seq;
+                // A tiles of this row tile (the previous item's MMAs must have drained first)
+                if (item_no > 0) mbar_wait(mma_done, (uint32_t)(item_no - 1) & 1u);
+                mbar_arrive_expect_tx(a_full, 2 * kABytes);
+#pragma unroll
+                for (int a = 0; a < KA; ++a) {
+                    tma_load_2d(sA0 + a * kTcRows * 128, &mapZ0, a_full, 32 * a, zt * kTcRows);
+                    tma_load_2d(sA1 + a * kTcRows * 128, &mapZ1, a_full, 32 * a, zt * kTcRows);
+                }
+                // tile q of the item: sequences in pairs (set 0 takes the even ones of the chunk), tiles of both interleaved
+                auto tile_of = [&](long long q, int& set, long long& nseq, int& tt) {
+                    const long long per_pair = 2LL * tiles_per_seq;
+                    const long long pi = q / per_pair, r = q - pi * per_pair;
+                    const long long na = n0 + 2 * pi;
+                    if (na + 1 < n1) { set = (int)(r & 1); tt = (int)(r >> 1); nseq = na + set; }
+                    else { set = 0; tt = (int)r; nseq = na; }  // odd tail: one sequence, tiles_per_seq tiles
+                };
+                auto issue_load = [&](long long q) {
+                    int set, tt; long long nseq;
+                    tile_of(q, set, nseq, tt);
+                    const int st = (int)(ld_idx % S);
+                    mbar_wait(b_empty + 8 * st, (uint32_t)((ld_idx / S) & 1) ^ 1u);
+                    mbar_arrive_expect_tx(b_full + 8 * st, kBBytes);
+#pragma unroll
+                    for (int a = 0; a < KA; ++a)
+                        tma_load_2d(sB + st * kBBytes + a * kTcNT * 128, &mapX, b_full + 8 * st, 32 * a,
+                                    (int)(nseq * p.Lp + (long long)tt * kTcNT));
+                    ++ld_idx;
+                };
+                long long loaded = 0;
+                for (; loaded < ntile_item && loaded < S - 1; ++loaded) issue_load(loaded);
+                mbar_wait(a_full, (uint32_t)item_no & 1u);
+                for (long long q = 0; q < ntile_item; ++q) {
+                    if (loaded < ntile_item) { issue_load(loaded); ++loaded; }
+                    int set, tt; long long nseq;
+                    tile_of(q, set, nseq, tt);
+                    const int st = (int)(mma_idx % S);
+                    const int buf = (int)(cnt[set] & 1);
+                    mbar_wait(t_empty + 8 * (set * 2 + buf), (uint32_t)((cnt[set] >> 1) & 1) ^ 1u);  // epilogue drained the buffer
+                    mbar_wait(b_full + 8 * st, (uint32_t)((mma_idx / S) & 1));                       // the time steps have landed
+                    tc_fence_after();
+                    const uint32_t d0 = tmem_base + (uint32_t)((set * 2 + buf) * 128), d1 = d0 + kTcNT;
+#pragma unroll
+                    for (int ks = 0; ks < 4 * KA; ++ks) {
+                        const uint32_t off = (uint32_t)(ks >> 2) * 128u;  // atom
+                        const uint64_t bd = tc_smem_desc(sB + st * kBBytes + (ks >> 2) * kTcNT * 128 + (ks & 3) * 32);
+                        tc_mma_tf32(d0, tc_smem_desc(sA0 + off * kTcRows + (ks & 3) * 32), bd, kTcIdesc, ks > 0);
+                    }
+#pragma unroll
+                    for (int ks = 0; ks < 4 * KA; ++ks) {
+                        const uint32_t off = (uint32_t)(ks >> 2) * 128u;
+                        const uint64_t bd = tc_smem_desc(sB + st * kBBytes + (ks >> 2) * kTcNT * 128 + (ks & 3) * 32);
+                        tc_mma_tf32(d1, tc_smem_desc(sA1 + off * kTcRows + (ks & 3) * 32), bd, kTcIdesc, ks > 0);
+                    }
+                    tc_commit(b_empty + 8 * st);                    // the ring stage is free once these MMAs have read it
+                    tc_commit(t_full + 8 * (set * 2 + buf));        // ... and the accumulators are complete
+                    ++mma_idx;
+                    ++cnt[set];
+                }
+                tc_commit(mma_done);
+            }
+        }
+    } else {
+        // ===== epilogue: warp set `set`, TMEM lane quarter `quarter` =================================================
+        const int set = warp >> 2, quarter = warp & 3;
+        float* xb = xpatch + warp * 33 * kTcXPitch;
+        const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+        long long cnt = 0;  // tiles consumed by this set
+        const long long per = p.nz * p.n;
+        for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const int zt = (int)(item / p.nch), ch = (int)(item - (long long)zt * p.nch);
+            const long long n0 = (long long)ch * p.chunk;
+            const long long n1 = n0 + p.chunk < p.n ? n0 + p.chunk : p.n;
+            const TcRow row = p.rows[(long long)zt * kTcRows + quarter * 32 + lane];
+            const bool pad = row.m == 0;
+            const bool last = !pad && row.p == row.m - 1;
+            const int src = (pad || row.p == 0) ? 32 : lane - 1;  // whose prefix this lane multiplies by (32 = the ones row)
+            for (long long nseq = n0 + set; nseq < n1; nseq += 2) {
+                float carry = 0.f, vprev = 0.f;
+                for (int tt = 0; tt < tiles_per_seq; ++tt, ++cnt) {
+                    const int buf = (int)(cnt & 1);
+                    mbar_wait(t_full + 8 * (set * 2 + buf), (uint32_t)((cnt >> 1) & 1));
+                    tc_fence_after();
+                    const uint32_t d0 = tmem_base + lane_base + (uint32_t)((set * 2 + buf) * 128);
+#pragma unroll 1
+                    for (int sb = 0; sb < kTcNT / kTcNB; ++sb) {
+                        float a0[kTcNB], a1[kTcNB], h[kTcNB];
+                        tc_ld16(d0 + sb * kTcNB, a0);
+                        tc_ld16(d0 + kTcNT + sb * kTcNB, a1);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int t = 0; t < kTcNB; ++t) {
+                            const float v = tc_ex2(a1[t]) - tc_ex2(a0[t]);      // kernels.py:330
+                            if (tt == 0 && sb == 0 && t == 0) vprev = v;          // first time step: no increment yet
+                            h[t] = pad ? 0.f : v - vprev;                        // signature_algs.py:114
+                            vprev = v;
+                        }
+                        // NLEV rounds: after round j the lanes at chain position <= j hold their final r
+                        float cin[kTcNB], c[kTcNB];
+#pragma unroll
+                        for (int t = 0; t < kTcNB; ++t) cin[t] = 1.f;
+                        float run = carry;
+#pragma unroll
+                        for (int j = 0; j < NLEV; ++j) {
+                            run = carry;
+#pragma unroll
+                            for (int t = 0; t < kTcNB; ++t) {
+                                c[t] = run;                                      // exclusive prefix (signature_algs.py:123)
+                                run = fmaf(h[t], cin[t], run);
+                            }
+                            if (j + 1 < NLEV) {
+                                float4* w4 = reinterpret_cast<float4*>(xb + lane * kTcXPitch);
+#pragma unroll
+                                for (int t4 = 0; t4 < kTcNB / 4; ++t4) w4[t4] = make_float4(c[4 * t4], c[4 * t4 + 1], c[4 * t4 + 2], c[4 * t4 + 3]);
+                                __syncwarp();
+                                const float4* r4 = reinterpret_cast<const float4*>(xb + src * kTcXPitch);
+#pragma unroll
+                                for (int t4 = 0; t4 < kTcNB / 4; ++t4) {
+                                    const float4 q4 = r4[t4];
+                                    cin[4 * t4] = q4.x; cin[4 * t4 + 1] = q4.y; cin[4 * t4 + 2] = q4.z; cin[4 * t4 + 3] = q4.w;
+                                }
+                                __syncwarp();
+                            }
+                        }
+                        carry = run;
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(t_empty + 8 * (set * 2 + buf));
+                }
+                if (last) {
+                    const long long idx = (long long)row.z * p.n + nseq;
+                    p.out[(long long)row.m * per + idx] = carry;               // signature_algs.py:125
+                    if (row.m == 1) p.out[idx] = 1.f;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---- operand preparation --------------------------------------------------------------------------------------------
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void tf32_split3(float v, float& p1, float& p2, float& p3) {
+    p1 = tf32_rn(v);
+    const float r = v - p1;
+    p2 = tf32_rn(r);
+    p3 = tf32_rn(r - p2);
+}
+
+// column sums of the scaled points (for the centre): sums[c] += sum over rows of X[r, c] * inv_ls[c]
+__global__ void tc_centre_kernel(const float* __restrict__ X, long long rows, int d, const float* __restrict__ inv_ls,
+                                 float* __restrict__ sums) {
+    for (int c = 0; c < d; ++c) {
+        float acc = 0.f;
+        for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x)
+            acc += X[r * d + c] * (inv_ls ? inv_ls[c] : 1.f);
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(sums + c, acc);
+    }
+}
+
+// B operand: one row per (sequence, padded time step); rows past the end of a sequence repeat its last point
+__global__ void tc_prep_x_kernel(const float* __restrict__ X, long long n, int L, int Lp, int d, const float* __restrict__ inv_ls,
+                                 const float* __restrict__ sums, int KW, float* __restrict__ out, unsigned* __restrict__ flag) {
+    const float rs = 0.8493218002880191f;  // sqrt(log2(e) / 2): log2 k = -|x' - z'|^2
+    const float inv_rows = 1.f / (float)(n * L);
+    float worst = 0.f;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n * Lp; idx += (long long)gridDim.x * blockDim.x) {
+        const long long seq = idx / Lp;
+        int t = (int)(idx - seq * Lp);
+        if (t > L - 1) t = L - 1;
+        const float* x0 = X + (seq * L + t) * d;
+        float* o = out + idx * KW;
+        float nn = 0.f;
+        for (int c = 0; c < d; ++c) {
+            const float s = inv_ls ? inv_ls[c] : 1.f;
+            const float v = (x0[c] * s - sums[c] * inv_rows) * rs;
+            nn = fmaf(v, v, nn);
+            const float hi = tf32_rn(v), lo = tf32_rn(v - hi);
+            o[c] = hi; o[d + c] = lo; o[2 * d + c] = hi;
+        }
+        float p1, p2, p3;
+        tf32_split3(-nn, p1, p2, p3);
+        o[3 * d] = p1; o[3 * d + 1] = p2; o[3 * d + 2] = p3;
+        o[3 * d + 3] = 1.f; o[3 * d + 4] = 1.f; o[3 * d + 5] = 1.f;
+        for (int c = 3 * d + 6; c < KW; ++c) o[c] = 0.f;
+        worst = fmaxf(worst, nn);
+    }
+    for (int o2 = 16; o2 > 0; o2 >>= 1) worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, o2));
+    if ((threadIdx.x & 31) == 0 && worst > 0.f) atomicMax(flag, __float_as_uint(worst));
+}
+
+// A operands: row r of the row map -> the z^0 (w = 0) and z^1 (w = 1) points of its (tensor, component); padding rows are zero
+__global__ void tc_prep_z_kernel(const float* __restrict__ Z, long long nz, int d, const float* __restrict__ inv_ls,
+                                 const float* __restrict__ sums, float inv_rows, const TcRow* __restrict__ rows, long long nrows,
+                                 int KW, float* __restrict__ out0, float* __restrict__ out1) {
+    const float rs = 0.8493218002880191f;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < 2 * nrows; idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx >> 1;
+        const int w = (int)(idx & 1);
+        float* o = (w ? out1 : out0) + r * KW;
+        const TcRow row = rows[r];
+        if (row.m == 0) {
+            for (int c = 0; c < KW; ++c) o[c] = 0.f;
+            continue;
+        }
+        const float* z0 = Z + (((long long)row.k * nz + row.z) * 2 + w) * d;
+        float nn = 0.f;
+        for (int c = 0; c < d; ++c) {
+            const float s = inv_ls ? inv_ls[c] : 1.f;
+            const float v = (z0[c] * s - sums[c] * inv_rows) * rs;
+            nn = fmaf(v, v, nn);
+            const float v2 = v + v;
+            const float hi = tf32_rn(v2), lo = tf32_rn(v2 - hi);
+            o[c] = hi; o[d + c] = hi; o[2 * d + c] = lo;
+        }
+        float p1, p2, p3;
+        tf32_split3(-nn, p1, p2, p3);
+        o[3 * d] = 1.f; o[3 * d + 1] = 1.f; o[3 * d + 2] = 1.f;
+        o[3 * d + 3] = p1; o[3 * d + 4] = p2; o[3 * d + 5] = p3;
+        for (int c = 3 * d + 6; c < KW; ++c) o[c] = 0.f;
+    }
+}
+
+// ---- host ----------------------------------------------------------------------------------------------------------
+// chains (tensor, level) packed into warps of 32 rows, never split
+static void tc_row_map(long long nz, int nlev, std::vector<TcRow>& rows) {
+    rows.clear();
+    int used = 0;  // rows used in the current warp
+    auto pad_to_warp = [&]() { while (used % 32) { rows.push_back(TcRow{0, 0, 0, 0}); ++used; } };
+    for (long long z = 0; z < nz; ++z)
+        for (int m = nlev; m >= 1; --m) {
+            if ((used % 32) + m > 32) pad_to_warp();
+            const int k0 = m * (m - 1) / 2;
+            for (int q = 0; q < m; ++q) { rows.push_back(TcRow{(int)z, m, q, k0 + q}); ++used; }
+        }
+    while (rows.size() % kTcRows) rows.push_back(TcRow{0, 0, 0, 0});
+}
+
+bool tens_tc_supported(int kind, int d, int nlev, int order, int increments, int difference, int L) {
+    return kind == GPSIG_KERN_RBF && order == 1 && increments && difference && nlev >= 1 && nlev <= 6 && 3 * d + 6 <= 64 && L >= 2 &&
+           env_knobs().tens_tc != 0;
+}
+
+template <int NLEV, int KA>
+static int launch_tc_inst(const CUtensorMap& mx, const CUtensorMap& mz0, const CUtensorMap& mz1, const TcParams& p, cudaStream_t st) {
+    constexpr int S = KA == 1 ? 6 : 4;
+    auto kern = tens_seq_tc_kernel<NLEV, KA, S>;
+    const size_t smem = 2 * (size_t)KA * kTcRows * 128 + (size_t)S * KA * kTcNT * 128 + 8 * 33 * kTcXPitch * 4 + 16 * S + 80 + 16 + 1024;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const long long nitems = (long long)p.ntiles * p.nch;
+    const int grid = (int)(nitems < num_sms() ? nitems : num_sms());
+    kern<<<grid, 288, smem, st>>>(mx, mz0, mz1, p);
+    return check_launch();
+}
+
+template <int KA>
+static int launch_tc_lev(int nlev, const CUtensorMap& mx, const CUtensorMap& mz0, const CUtensorMap& mz1, const TcParams& p,
+                         cudaStream_t st) {
+    switch (nlev) {
+        case 1: return launch_tc_inst<1, KA>(mx, mz0, mz1, p, st);
+        case 2: return launch_tc_inst<2, KA>(mx, mz0, mz1, p, st);
+        case 3: return launch_tc_inst<3, KA>(mx, mz0, mz1, p, st);
+        case 4: return launch_tc_inst<4, KA>(mx, mz0, mz1, p, st);
+        case 5: return launch_tc_inst<5, KA>(mx, mz0, mz1, p, st);
+        case 6: return launch_tc_inst<6, KA>(mx, mz0, mz1, p, st);
+    }
+    return GPSIG_E_UNSUPPORTED;
+}
+
+// Z (T, nz, 2, d), X (n, L, d) RAW; inv_ls may be NULL; out (nlev + 1, nz, n); flag: one device word (written here)
+int launch_tens_seq_tc(const float* Z, long long nz, const float* X, long long n, int L, int d, const float* inv_ls, int nlev,
+                       float* out, unsigned* flag, cudaStream_t st) {
+    const int KA = 3 * d + 6 <= 32 ? 1 : 2, KW = 32 * KA;
+    const int Lp = (L + kTcNT - 1) / kTcNT * kTcNT;
+    std::vector<TcRow> rows;
+    tc_row_map(nz, nlev, rows);
+    const long long nrows = (long long)rows.size();
+    const int ntiles = (int)(nrows / kTcRows);
+    // scratch: sums (d floats, zeroed) | row map | Xop | Z0op | Z1op
+    auto up = [](size_t x) { return (x + 1023) / 1024 * 1024; };
+    const size_t b_sums = up(64 * 4), b_rows = up((size_t)nrows * sizeof(TcRow)), b_x = up((size_t)n * Lp * KW * 4),
+                 b_z = up((size_t)nrows * KW * 4);
+    uint8_t* buf = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&buf, b_sums + b_rows + b_x + 2 * b_z + 1024, st);
+    if (e != cudaSuccess) return (int)e;
+    uint8_t* w = (uint8_t*)(((uintptr_t)buf + 1023) / 1024 * 1024);
+    float* sums = (float*)w; w += b_sums;
+    TcRow* drows = (TcRow*)w; w += b_rows;
+    float* Xop = (float*)w; w += b_x;
+    float* Z0 = (float*)w; w += b_z;
+    float* Z1 = (float*)w;
+    int rc = GPSIG_OK;
+    auto done = [&](int code) { cudaFreeAsync(buf, st); return code; };
+    if ((e = cudaMemsetAsync(sums, 0, b_sums, st)) != cudaSuccess) return done((int)e);
+    if ((e = cudaMemsetAsync(flag, 0, sizeof(unsigned), st)) != cudaSuccess) return done((int)e);
+    // the row map is tiny (16 bytes per row) and a pure function of (nz, nlev): staged through the stream
+    if ((e = cudaMemcpyAsync(drows, rows.data(), (size_t)nrows * sizeof(TcRow), cudaMemcpyHostToDevice, st)) != cudaSuccess)
+        return done((int)e);
+    // cudaMemcpyAsync from pageable memory returns after the source has been staged, so `rows` may go out of scope
+    const int cap = num_sms() * 8;
+    {
+        const long long rowsX = n * L;
+        long long blocks = (rowsX + 255) / 256;
+        tc_centre_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(X, rowsX, d, inv_ls, sums);
+        if ((rc = check_launch())) return done(rc);
+        blocks = (n * Lp + 255) / 256;
+        tc_prep_x_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(X, n, L, Lp, d, inv_ls, sums, KW, Xop, flag);
+        if ((rc = check_launch())) return done(rc);
+        blocks = (2 * nrows + 255) / 256;
+        tc_prep_z_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(Z, nz, d, inv_ls, sums, 1.f / (float)rowsX, drows, nrows,
+                                                                             KW, Z0, Z1);
+        if ((rc = check_launch())) return done(rc);
+    }
+    CUtensorMap mx, mz0, mz1;
+    {
+        uint64_t dims[2] = {(uint64_t)KW, (uint64_t)(n * Lp)}, strides[1] = {(uint64_t)KW * 4};
+        uint32_t box[2] = {32, (uint32_t)kTcNT};
+        if ((rc = encode_tensor_map_f32(&mx, Xop, 2, dims, strides, box, 1))) return done(rc);
+        uint64_t dz[2] = {(uint64_t)KW, (uint64_t)nrows};
+        uint32_t bz[2] = {32, (uint32_t)kTcRows};
+        if ((rc = encode_tensor_map_f32(&mz0, Z0, 2, dz, strides, bz, 1))) return done(rc);
+        if ((rc = encode_tensor_map_f32(&mz1, Z1, 2, dz, strides, bz, 1))) return done(rc);
+    }
+    TcParams p;
+    p.rows = drows; p.flag = flag; p.ntiles = ntiles; p.nz = nz; p.n = n; p.Lp = Lp; p.out = out;
+    // chunks of sequences: enough items to balance 148 SMs (a few per SM), an even number of sequences per chunk
+    long long chunk = 64;
+    while (chunk > 8 && (long long)ntiles * ((n + chunk - 1) / chunk) < 4LL * num_sms()) chunk >>= 1;
+    p.chunk = (int)chunk;
+    p.nch = (int)((n + chunk - 1) / chunk);
+    {
+        ProfScope prof(GPSIG_PROF_TENS, st, (double)nz * n);
+        rc = KA == 1 ? launch_tc_lev<1>(nlev, mx, mz0, mz1, p, st) : launch_tc_lev<2>(nlev, mx, mz0, mz1, p, st);
+    }
+    return done(rc);
+}
+
+}  // namespace gpsig

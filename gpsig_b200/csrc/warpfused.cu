@@ -59,7 +59,7 @@ struct WfParams {
     float* out;
     long long out_level_stride;
     int xfloats, yfloats;  // per-warp tile sizes (floats): x tile (one buffer), y tile
-    int nufloats, ancfloats;  // RBF anchored: -|u|^2 tile (G * rowsB rounded up to 4) and anchor tile (G * LP * D)
+    int nufloats;          // RBF anchored: -|u|^2 tile, ONE buffer of G * 8 LP floats (double buffered like the x tile)
 };
 
 __device__ __forceinline__ float wf_ex2(float x) {
@@ -134,10 +134,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_warpfused_kernel(const W
     const long long total = nloc * Lrow;
     if (total == 0) return;
     const long long nsteps = total + LP - 1;
-    float* xt = wsm + (size_t)warp * (2 * p.xfloats + p.yfloats + p.nufloats + p.ancfloats);  // x tile, two buffers
+    float* xt = wsm + (size_t)warp * (2 * p.xfloats + p.yfloats + 2 * p.nufloats);  // x tile, two buffers
     float* yt = xt + 2 * p.xfloats;                                 // y tile of the item strip 0 entered last
-    float* nut = yt + p.yfloats;                                    // its -|u|^2 values and anchors (RBF anchored form)
-    float* anct = nut + p.nufloats;
+    float* nut = yt + p.yfloats;                                    // -|u|^2 of the column points, two buffers (read every step)
     const int l = lane & (LP - 1), q = lane >> p.log2LP;
     const int t0 = l * W;
     const int xq = p.diag ? q * Lrow * D : 0;  // diag: pair q reads its own row sequence
@@ -149,7 +148,6 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_warpfused_kernel(const W
     float PS = 0.f, KS = 0.f;           // level NLEV - 1 when NLEV is odd
     float2 y[W][H];      // LINEAR: dy_t;  RBF anchored: 2 (y_t - a);  RBF direct: -y_t
     float2 nanc[H];      // RBF anchored: minus the anchor a
-    float nu[W];         // RBF anchored: -|y_t - a|^2
     float2 gprev[W / 2]; // RBF: column differences f[s-1, t] - f[s-1, t-1] of the previous row
     float flast = 0.f;   // RBF: this lane's last column value of the previous step (the right neighbour's left halo)
 #pragma unroll
@@ -161,11 +159,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_warpfused_kernel(const W
         for (int i = 0; i < NAP; ++i) AP[i][j] = make_float2(0.f, 0.f);
     }
 #pragma unroll
-    for (int u = 0; u < W; ++u) {
-        nu[u] = 0.f;
+    for (int u = 0; u < W; ++u)
 #pragma unroll
         for (int h = 0; h < H; ++h) y[u][h] = make_float2(0.f, 0.f);
-    }
 #pragma unroll
     for (int u = 0; u < W / 2; ++u) gprev[u] = make_float2(0.f, 0.f);
 #pragma unroll
@@ -217,11 +213,11 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_warpfused_kernel(const W
                     if (jl > p.n2 - 1) jl = p.n2 - 1;  // padding pair of a ragged last group
                     const float4* srcy = reinterpret_cast<const float4*>(ysrc + (long long)jl * p.rowsB * D);
                     for (int e = lane; e < per; e += 32) dsty[g * per + e] = __ldg(srcy + e);
-                    if (MODE == 1) {
-                        for (int e = lane; e < p.rowsB; e += 32) nut[g * p.rowsB + e] = __ldg(p.Bnu + (long long)jl * p.rowsB + e);
-                        const float4* srca = reinterpret_cast<const float4*>(p.Banc + (long long)jl * p.nstrip * D);
-                        float4* dsta = reinterpret_cast<float4*>(anct) + g * LP * C4;
-                        for (int e = lane; e < p.nstrip * C4; e += 32) dsta[e] = __ldg(srca + e);
+                    if (MODE == 1) {  // -|u|^2 of every strip point (points past the end are copies of the last one)
+                        float* dn = nut + par0 * p.nufloats + g * LP * W;
+                        for (int e = lane; e < LP * W; e += 32)  // the tail of a partial strip repeats the last point; strips
+                            dn[e] = e < p.nstrip * W                // entirely past the end are anchored AT the last point
+                                        ? __ldg(p.Bnu + (long long)jl * p.rowsB + (e < p.rowsB ? e : p.rowsB - 1)) : 0.f;
                     }
                 }
             }
@@ -236,25 +232,31 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_warpfused_kernel(const W
         if (EV && valid && s == 0) {
             if (MODE == 1) {
                 // everything was put into the anchored form once per call (wf_anchor_prep_kernel): plain copies
-                const float4* sa = reinterpret_cast<const float4*>(anct) + (q * LP + l) * C4;
+                int jl = wf_track_jg(p, ty) * p.G + q;
+                if (jl > p.n2 - 1) jl = p.n2 - 1;
+                // a strip entirely past the end of the sequence stands for copies of the last point: anchored AT that point
+                // (u = 0 for every column, so that its anchor column evaluates the same value as the others)
+                const bool past = l >= p.nstrip;
+                const float4* sa = past ? reinterpret_cast<const float4*>(p.B + ((long long)jl * p.rowsB + p.rowsB - 1) * D)
+                                        : reinterpret_cast<const float4*>(p.Banc + ((long long)jl * p.nstrip + l) * D);
+                const float sgn = past ? -1.f : 1.f;  // Banc already holds -a
 #pragma unroll
                 for (int c = 0; c < C4; ++c) {
-                    const float4 v = sa[c];
-                    nanc[2 * c] = make_float2(v.x, v.y);
-                    nanc[2 * c + 1] = make_float2(v.z, v.w);
+                    const float4 v = __ldg(sa + c);
+                    nanc[2 * c] = make_float2(sgn * v.x, sgn * v.y);
+                    nanc[2 * c + 1] = make_float2(sgn * v.z, sgn * v.w);
                 }
 #pragma unroll
                 for (int u = 0; u < W; ++u) {
                     const int t = t0 + u;
-                    const int tc = t < p.rowsB ? t : p.rowsB - 1;  // clamp: equal points difference to exactly zero
+                    const int tc = t < p.rowsB ? t : p.rowsB - 1;  // tail of a partial strip: copies of the last point
                     const float4* src = reinterpret_cast<const float4*>(yt + ((size_t)q * p.rowsB + tc) * D);
 #pragma unroll
                     for (int c = 0; c < C4; ++c) {
-                        const float4 v = src[c];
+                        const float4 v = past ? make_float4(0.f, 0.f, 0.f, 0.f) : src[c];
                         y[u][2 * c] = make_float2(v.x, v.y);
                         y[u][2 * c + 1] = make_float2(v.z, v.w);
                     }
-                    nu[u] = nut[q * p.rowsB + tc];
                 }
             } else {
 #pragma unroll
@@ -301,105 +303,100 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_warpfused_kernel(const W
             }
         }
         // running row prefixes arrive from the strip to the left (it finished this row one step ago)
-        float pin[NLEV];
 #pragma unroll
         for (int m = 0; m < NLEV; ++m) {
-            pin[m] = __shfl_up_sync(0xffffffffu, Pm(m), 1);
-            if (first) pin[m] = 0.f;
+            const float pin = __shfl_up_sync(0xffffffffu, Pm(m), 1);
+            Pm(m) = first ? 0.f : pin;
         }
         float fl = 0.f;
         if (RBF) fl = __shfl_up_sync(0xffffffffu, flast, 1);
-        // ---- increments of row s of the strip ----
-        float2 d2[W / 2];
-#pragma unroll
-        for (int u = 0; u < W / 2; ++u) d2[u] = make_float2(0.f, 0.f);
+        // ---- row s of the strip, two columns at a time: evaluate -> difference -> recursion (nothing but the previous
+        //      column's value and the running prefixes is carried from one pair of columns to the next) ----
+        float2 x[H];
         if (valid) {
-            float2 x[H];
-            {
-                const float4* xs = reinterpret_cast<const float4*>(xt + par * p.xfloats + xq) + s * C4;
-                const int sw = (C4 == 2) ? ((s >> 2) & 1) : 0;
+            const float4* xs = reinterpret_cast<const float4*>(xt + par * p.xfloats + xq) + s * C4;
+            const int sw = (C4 == 2) ? ((s >> 2) & 1) : 0;
 #pragma unroll
-                for (int c = 0; c < C4; ++c) {
-                    const float4 v = xs[c ^ sw];
-                    x[2 * c] = make_float2(v.x, v.y);
-                    x[2 * c + 1] = make_float2(v.z, v.w);
-                }
+            for (int c = 0; c < C4; ++c) {
+                const float4 v = xs[c ^ sw];
+                x[2 * c] = make_float2(v.x, v.y);
+                x[2 * c + 1] = make_float2(v.z, v.w);
             }
+        } else {
+#pragma unroll
+            for (int h = 0; h < H; ++h) x[h] = make_float2(0.f, 0.f);
+        }
+        float nw = 0.f;      // MODE 1: |w|^2, and x[] holds w = x - a from here on
+        float nu[W];         // MODE 1: -|y_t - a|^2 of the strip's points (shared memory: registers are the scarce resource)
+        if (MODE == 1) {
+            const float4* nup = reinterpret_cast<const float4*>(nut + par * p.nufloats + (q * LP + l) * W);
+            const float4 n0 = nup[0], n1 = nup[1];
+            nu[0] = n0.x; nu[1] = n0.y; nu[2] = n0.z; nu[3] = n0.w;
+            nu[4] = n1.x; nu[5] = n1.y; nu[6] = n1.z; nu[7] = n1.w;
+#pragma unroll
+            for (int h = 0; h < H; ++h) x[h] = __fadd2_rn(x[h], nanc[h]);
+            float2 ww = __fmul2_rn(x[0], x[0]);
+#pragma unroll
+            for (int h = 1; h < H; ++h) ww = __ffma2_rn(x[h], x[h], ww);
+            nw = ww.x + ww.y;
+        }
+        auto eval = [&](int u) -> float {  // Gram value (RBF) / increment (LINEAR) of column u of this row
             if (MODE == 0) {
+                float2 acc = __fmul2_rn(x[0], y[u][0]);
 #pragma unroll
-                for (int u = 0; u < W; ++u) {
-                    float2 acc = __fmul2_rn(x[0], y[u][0]);
+                for (int h = 1; h < H; ++h) acc = __ffma2_rn(x[h], y[u][h], acc);
+                return acc.x + acc.y;
+            } else if (MODE == 1) {
+                if (u == kWfAnchor) return wf_ex2(-nw);
+                float2 acc = make_float2(nu[u] - nw, 0.f);
 #pragma unroll
-                    for (int h = 1; h < H; ++h) acc = __ffma2_rn(x[h], y[u][h], acc);
-                    if (u & 1) d2[u >> 1].y = acc.x + acc.y; else d2[u >> 1].x = acc.x + acc.y;
-                }
+                for (int h = 0; h < H; ++h) acc = __ffma2_rn(x[h], y[u][h], acc);
+                return wf_ex2(acc.x + acc.y);
             } else {
-                float f[W];
-                if (MODE == 1) {
-                    float2 w[H];
+                float2 df = __fadd2_rn(x[0], y[u][0]);
+                float2 acc = __fmul2_rn(df, df);
 #pragma unroll
-                    for (int h = 0; h < H; ++h) w[h] = __fadd2_rn(x[h], nanc[h]);
-                    float2 ww = __fmul2_rn(w[0], w[0]);
-#pragma unroll
-                    for (int h = 1; h < H; ++h) ww = __ffma2_rn(w[h], w[h], ww);
-                    const float nw = ww.x + ww.y;  // |w|^2
-#pragma unroll
-                    for (int u = 0; u < W; ++u) {
-                        if (u == kWfAnchor) {
-                            f[u] = wf_ex2(-nw);
-                        } else {
-                            float2 acc = make_float2(nu[u] - nw, 0.f);
-#pragma unroll
-                            for (int h = 0; h < H; ++h) acc = __ffma2_rn(w[h], y[u][h], acc);
-                            f[u] = wf_ex2(acc.x + acc.y);
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int u = 0; u < W; ++u) {
-                        float2 df = __fadd2_rn(x[0], y[u][0]);
-                        float2 acc = __fmul2_rn(df, df);
-#pragma unroll
-                        for (int h = 1; h < H; ++h) {
-                            df = __fadd2_rn(x[h], y[u][h]);
-                            acc = __ffma2_rn(df, df, acc);
-                        }
-                        f[u] = wf_ex2(-(acc.x + acc.y));
-                    }
+                for (int h = 1; h < H; ++h) {
+                    df = __fadd2_rn(x[h], y[u][h]);
+                    acc = __ffma2_rn(df, df, acc);
                 }
-                // lane l owns the increment columns 8 l - 1 .. 8 l + 6 (column -1 is a zero pad): the value to the LEFT of
-                // its first point belongs to lane l - 1, which evaluated this very row one step ago
-                float2 g[W / 2];
-                g[0] = make_float2(f[0] - fl, f[1] - f[0]);
+                return wf_ex2(-(acc.x + acc.y));
+            }
+        };
+        float fcol = fl;     // RBF: value of the column to the left (lane l owns the increment columns 8 l - 1 .. 8 l + 6; the
+                             // value left of its first point belongs to lane l - 1, which evaluated this row one step ago)
+        const bool live = valid && (!RBF || !EV || s > 0);  // RBF: the first row of an item only primes the differencing
 #pragma unroll
-                for (int u = 1; u < W / 2; ++u) g[u] = make_float2(f[2 * u] - f[2 * u - 1], f[2 * u + 1] - f[2 * u]);
-                if (!EV || s > 0) {
-                    const float2 m1 = make_float2(-1.f, -1.f);
+        for (int up = 0; up < W / 2; ++up) {
+            const float f0 = eval(2 * up), f1 = eval(2 * up + 1);
+            float2 dd;
+            if (RBF) {
+                const float2 g = make_float2(f0 - fcol, f1 - f0);
+                fcol = f1;
+                dd = __ffma2_rn(gprev[up], make_float2(-1.f, -1.f), g);
+                if (valid) gprev[up] = g;
+                if (up == 0 && first) dd.x = 0.f;  // column -1 is a zero pad
+            } else {
+                dd = make_float2(f0, f1);
+            }
+            if (!live) dd = make_float2(0.f, 0.f);
+            // the recursion: 2 FP ops per entry per level
 #pragma unroll
-                    for (int u = 0; u < W / 2; ++u) d2[u] = __ffma2_rn(gprev[u], m1, g[u]);
-                    if (first) d2[0].x = 0.f;
-                }
+            for (int e = 0; e < 2; ++e) {
+                const int j = 2 * up + e;
+                const float dj = e ? dd.y : dd.x;
+                float pn[NLEV];  // p_m after this column (levels >= 1 read the OLD A_{m-1} and the OLD p_m)
 #pragma unroll
-                for (int u = 0; u < W / 2; ++u) gprev[u] = g[u];
-                flast = f[W - 1];
+                for (int m = 1; m < NLEV; ++m) pn[m] = fmaf(dj, Am(m - 1, j), Pm(m));
+                pn[0] = Pm(0) + dj;
+#pragma unroll
+                for (int i = 0; i < NAP; ++i) AP[i][j] = __fadd2_rn(AP[i][j], PP[i]);
+                if (NA & 1) AS[j] += Pm(NA - 1);
+#pragma unroll
+                for (int m = 0; m < NLEV; ++m) Pm(m) = pn[m];
             }
         }
-        // ---- the recursion: 2 FP ops per entry per level ----
-#pragma unroll
-        for (int m = 0; m < NLEV; ++m) Pm(m) = pin[m];
-#pragma unroll
-        for (int j = 0; j < W; ++j) {
-            const float dj = (j & 1) ? d2[j >> 1].y : d2[j >> 1].x;
-            float pn[NLEV];  // p_m after this column (levels >= 1 read the OLD A_{m-1} and the OLD p_m)
-#pragma unroll
-            for (int m = 1; m < NLEV; ++m) pn[m] = fmaf(dj, Am(m - 1, j), Pm(m));
-            pn[0] = Pm(0) + dj;
-#pragma unroll
-            for (int i = 0; i < NAP; ++i) AP[i][j] = __fadd2_rn(AP[i][j], PP[i]);
-            if (NA & 1) AS[j] += Pm(NA - 1);
-#pragma unroll
-            for (int m = 0; m < NLEV; ++m) Pm(m) = pn[m];
-        }
+        if (RBF && valid) flast = fcol;
         if (valid) {
 #pragma unroll
             for (int i = 0; i < NPP; ++i) KP[i] = __fadd2_rn(KP[i], PP[i]);
@@ -521,7 +518,7 @@ bool warpfused_supported(bool rbf, int d, int nlev, int ncols, int rowsA) {
 template <int MODE, int NLEV, int D, int MAXW>
 static int launch_wf_maxw(WfParams& p, cudaStream_t st) {
     auto kern = sigkern_warpfused_kernel<MODE, NLEV, D, MAXW>;
-    const size_t per_warp = (size_t)(2 * p.xfloats + p.yfloats + p.nufloats + p.ancfloats) * sizeof(float);
+    const size_t per_warp = (size_t)(2 * p.xfloats + p.yfloats + 2 * p.nufloats) * sizeof(float);
     int nw = MAXW;
     if (env_knobs().warpfused_warps > 0 && env_knobs().warpfused_warps < nw) nw = env_knobs().warpfused_warps;
     while (nw > 1 && per_warp * nw > 232448) --nw;
@@ -540,6 +537,8 @@ static int launch_wf_maxw(WfParams& p, cudaStream_t st) {
 template <int MODE, int D>
 static int launch_wf_lev(int nlev, WfParams& p, cudaStream_t st) {
     constexpr int MAXW = (MODE == 0 || MODE == 1) ? 12 : 8;
+    if (nlev == 5 && MAXW == 12 && env_knobs().warpfused_warps == 8)  // experiment: 8 warps with the 255-register budget
+        return launch_wf_maxw<MODE, 5, D, 8>(p, st);
     switch (nlev) {
         case 2: return launch_wf_maxw<MODE, 2, D, MAXW>(p, st);
         case 3: return launch_wf_maxw<MODE, 3, D, MAXW>(p, st);
@@ -590,19 +589,18 @@ int launch_sigkern_warpfused(bool rbf, const float* A, const float* B, const WfA
     if (rbf) {
         // anchored instantiation: y tile + -|u|^2 tile + anchor tile;  direct instantiation: plain y tile (diag: none)
         p.yfloats = p.G * rowsB * D;
-        p.nufloats = (p.G * rowsB + 3) / 4 * 4;
-        p.ancfloats = p.G * p.LP * D;
+        p.nufloats = p.G * p.LP * kWfCols;
         if (D == 4) rc = launch_wf_lev<1, 4>(nlev, p, st);
         if (D == 8) rc = launch_wf_lev<1, 8>(nlev, p, st);
         if (!rc && flag) {
             p.yfloats = diag ? 0 : p.G * rowsB * D;
-            p.nufloats = p.ancfloats = 0;
+            p.nufloats = 0;
             if (D == 4) rc = launch_wf_lev<2, 4>(nlev, p, st);
             if (D == 8) rc = launch_wf_lev<2, 8>(nlev, p, st);
         }
     } else {
         p.yfloats = diag ? 0 : p.G * rowsB * D;
-        p.nufloats = p.ancfloats = 0;
+        p.nufloats = 0;
         if (D == 4) rc = launch_wf_lev<0, 4>(nlev, p, st);
         if (D == 8) rc = launch_wf_lev<0, 8>(nlev, p, st);
     }

@@ -236,3 +236,32 @@ def test_wide_state_space_falls_back_to_the_materialised_gram(kind):
     r, ro = k.K_tens_n_seq_covs(Z, X, increments=True), ko.K_tens_n_seq_covs(Z, X, increments=True)
     for a, b, nm in zip(r, ro, ("zz", "zx", "xx")):
         assert_close(a.cpu().numpy(), b, msg=nm)
+
+
+def test_gram_with_more_rows_than_a_grid_dimension():
+    """gpsig_gram put the rows on gridDim.y (cap 65535 blocks of 8): the low-rank mode's Nystrom map calls it
+    with N L rows.  700k rows against 50 landmarks."""
+    from gpsig_b200 import kernels
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((700_000, 3))
+    B = rng.standard_normal((50, 3))
+    k = kernels.SignatureRBF(3, 3, 2, lengthscales=None)
+    G = k._base_gram(torch.as_tensor(A, dtype=torch.float32, device="cuda"), torch.as_tensor(B, dtype=torch.float32, device="cuda"))
+    rows = np.array([0, 1, 65535 * 8 - 1, 65535 * 8, 65535 * 8 + 7, 699_999])
+    ref = np.exp(-0.5 * ((A[rows][:, None, :] - B[None, :, :]) ** 2).sum(-1))
+    assert_close(G[torch.as_tensor(rows, device="cuda")].cpu().numpy(), ref, tol=1e-5, msg="gram rows")
+
+
+def test_diag_pass_of_many_short_sequences_on_a_fresh_kernel():
+    """the diagonal pass keeps the prepared points of ALL sequences in its workspace; a fresh kernel object (no
+    cached workspace from an earlier K call) with 20000 sequences of 10 points."""
+    n, L, d, M = 20000, 10, 4, 3
+    X = random_walks(n, L, d, 5).reshape(n, -1)
+    for kind in ("rbf", "linear"):
+        k, ko = _pair(kind, L, d, M, normalization=False)
+        got = k.Kdiag(X, return_levels=True).cpu().numpy()
+        sel = np.array([0, 1, 7777, n - 1])
+        assert_levels_close(got[:, sel], ko.Kdiag(X[sel], return_levels=True), msg="diag %s" % kind)
+        k2, _ = _pair(kind, L, d, M)
+        Z = 0.5 * np.random.default_rng(1).standard_normal((M * (M + 1) // 2, 3, 2, d))
+        assert k2.K_tens_vs_seq(Z, X, increments=True).shape == (3, n)
