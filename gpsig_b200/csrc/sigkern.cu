@@ -561,6 +561,192 @@ int launch_sigkern_fo(const float* M, int n1, int Lrows, int n2, int ncols, int 
     return check_launch();
 }
 
+// Higher-order recursion, one WARP per pair (the path with a number: notebooks/signature_kernel.ipynb runs order = M).
+// Lane l owns the WC columns [l WC, (l + 1) WC); rows are swept in lockstep, level by level inside a row:
+//   * the grid R_m[a][b] of the row lives in registers (D x D x WC values for the current and the next level);
+//   * AA_m (2-D exclusive prefix of sum_ab R_m) and V_m^k (exclusive column prefix of sum_a R_m[a][k]) are per-column
+//     registers carried down the rows;
+//   * H_m^j (exclusive ROW prefix of sum_b R_m[j][b]) and the row prefix that feeds AA_m are warp scans of the row
+//     (local prefix + 5-step shuffle scan of the lane totals): at most D scans per level per row.
+// Instantiated for D * D * WC <= 64 (order <= 5 at 64 columns, order <= 4 at 128); other shapes take the serial kernel.
+__device__ __forceinline__ float ho_warp_excl_prefix(float tot, int lane) {
+    float incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const float ex = __shfl_up_sync(0xffffffffu, incl, 1);
+    return lane == 0 ? 0.f : ex;
+}
+
+template <int NLEV, int D, int WC>
+__global__ void __launch_bounds__(128) sigkern_ho_warp_kernel(const HoParams p) {
+    constexpr int NA = NLEV > 1 ? NLEV - 1 : 1;
+    constexpr int DV = D > 1 ? D - 1 : 1;
+    const int lane = threadIdx.x & 31;
+    const long long npairs = (long long)p.n1 * p.n2;
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    const int c0 = lane * WC;
+    for (long long pr = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pr < npairs; pr += warps) {
+        const int i = (int)(pr / p.n2), j = (int)(pr % p.n2);
+        if (p.upper_only && p.j_off + j < p.i_off + i) continue;
+        const float* T = p.M + i * p.si + j * p.sj;
+        float AA[NA][WC], V[NA][DV][WC], K[NLEV];
+#pragma unroll
+        for (int m = 0; m < NLEV; ++m) K[m] = 0.f;
+#pragma unroll
+        for (int m = 0; m < NA; ++m)
+#pragma unroll
+            for (int c = 0; c < WC; ++c) {
+                AA[m][c] = 0.f;
+#pragma unroll
+                for (int k = 0; k < DV; ++k) V[m][k][c] = 0.f;
+            }
+        float raw0[WC + 1];  // difference: the previous raw Gram row (with the right-hand halo column)
+#pragma unroll
+        for (int c = 0; c <= WC; ++c) raw0[c] = (p.difference && c0 + c <= p.nc) ? T[c0 + c] : 0.f;
+        for (int r = 0; r < p.nr; ++r) {
+            float d[WC];
+            if (p.difference) {
+                const float* row1 = T + (long long)(r + 1) * p.ss;
+                float raw1[WC + 1];
+#pragma unroll
+                for (int c = 0; c <= WC; ++c) raw1[c] = (c0 + c <= p.nc) ? row1[c0 + c] : 0.f;
+#pragma unroll
+                for (int c = 0; c < WC; ++c) d[c] = (c0 + c < p.nc) ? (raw1[c + 1] - raw1[c]) - (raw0[c + 1] - raw0[c]) : 0.f;
+#pragma unroll
+                for (int c = 0; c <= WC; ++c) raw0[c] = raw1[c];
+            } else {
+                const float* row0 = T + (long long)r * p.ss;
+#pragma unroll
+                for (int c = 0; c < WC; ++c) d[c] = (c0 + c < p.nc) ? row0[c0 + c] : 0.f;
+            }
+            float Rc[D][D][WC];
+#pragma unroll
+            for (int c = 0; c < WC; ++c) { Rc[0][0][c] = d[c]; K[0] += d[c]; }
+#pragma unroll
+            for (int m = 1; m < NLEV; ++m) {  // source level m (grid size dc) -> level m + 1 (grid size dn)
+                constexpr int dummy = 0; (void)dummy;
+                const int dc = m < D ? m : D, dn = (m + 1 < D) ? m + 1 : D;
+                float Rn[D][D][WC];
+                // [1][1]: Delta * AA_m, then AA_m += exclusive row prefix of the level-m totals
+                float tot[WC], run = 0.f, pre[WC];
+#pragma unroll
+                for (int c = 0; c < WC; ++c) {
+                    float t = 0.f;
+#pragma unroll
+                    for (int a = 0; a < D; ++a)
+#pragma unroll
+                        for (int b = 0; b < D; ++b)
+                            if (a < dc && b < dc) t += Rc[a][b][c];
+                    tot[c] = t;
+                    pre[c] = run;
+                    run += t;
+                }
+                {
+                    const float off = ho_warp_excl_prefix(run, lane);
+#pragma unroll
+                    for (int c = 0; c < WC; ++c) {
+                        Rn[0][0][c] = d[c] * AA[m - 1][c];
+                        AA[m - 1][c] += off + pre[c];
+                    }
+                }
+#pragma unroll
+                for (int k = 2; k <= D; ++k) {
+                    if (k > dn) continue;
+                    // [1][k]: Delta * V_m^{k-1} / k, then V_m^{k-1} += sum_a R_m[a][k-1]
+#pragma unroll
+                    for (int c = 0; c < WC; ++c) {
+                        Rn[0][k - 1][c] = d[c] * V[m - 1][k - 2][c] * (1.f / (float)k);
+                        float cs = 0.f;
+#pragma unroll
+                        for (int a = 0; a < D; ++a)
+                            if (a < dc) cs += Rc[a][k - 2][c];
+                        V[m - 1][k - 2][c] += cs;
+                    }
+                    // [k][1]: Delta * H_m^{k-1} / k with H the exclusive row prefix of sum_b R_m[k-1][b]
+                    float rs[WC], rrun = 0.f, rpre[WC];
+#pragma unroll
+                    for (int c = 0; c < WC; ++c) {
+                        float t = 0.f;
+#pragma unroll
+                        for (int b = 0; b < D; ++b)
+                            if (b < dc) t += Rc[k - 2][b][c];
+                        rs[c] = t;
+                        rpre[c] = rrun;
+                        rrun += t;
+                    }
+                    const float roff = ho_warp_excl_prefix(rrun, lane);
+#pragma unroll
+                    for (int c = 0; c < WC; ++c) Rn[k - 1][0][c] = d[c] * (roff + rpre[c]) * (1.f / (float)k);
+                    // [k][k']: Delta * R_m[k-1][k'-1] / (k k')
+#pragma unroll
+                    for (int k2 = 2; k2 <= D; ++k2) {
+                        if (k2 > dn) continue;
+#pragma unroll
+                        for (int c = 0; c < WC; ++c) Rn[k - 1][k2 - 1][c] = d[c] * Rc[k - 2][k2 - 2][c] * (1.f / (float)(k * k2));
+                    }
+                }
+#pragma unroll
+                for (int a = 0; a < D; ++a)
+#pragma unroll
+                    for (int b = 0; b < D; ++b)
+#pragma unroll
+                        for (int c = 0; c < WC; ++c) {
+                            Rc[a][b][c] = (a < dn && b < dn) ? Rn[a][b][c] : 0.f;
+                            if (a < dn && b < dn) K[m] += Rn[a][b][c];
+                        }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < NLEV; ++m)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) K[m] += __shfl_xor_sync(0xffffffffu, K[m], o);
+        if (lane == 0) {
+            float* o = p.out + (long long)(p.i_off + i) * p.ldo + p.j_off + j;
+            o[0] = 1.f;
+#pragma unroll
+            for (int m = 0; m < NLEV; ++m) o[(long long)(m + 1) * p.out_level_stride] = K[m];
+        }
+    }
+}
+
+template <int NLEV, int D, int WC>
+static int launch_ho_warp_inst(const HoParams& h, cudaStream_t st) {
+    const long long npairs = (long long)h.n1 * h.n2;
+    long long blocks = (npairs + 3) / 4;
+    const long long cap = (long long)num_sms() * 8;
+    sigkern_ho_warp_kernel<NLEV, D, WC><<<(int)(blocks < cap ? blocks : cap), 128, 0, st>>>(h);
+    return check_launch();
+}
+
+template <int NLEV, int D>
+static int launch_ho_warp_wc(const HoParams& h, cudaStream_t st) {
+    const int wc = (h.nc + 31) / 32;
+    if (wc <= 1) return launch_ho_warp_inst<NLEV, D, 1>(h, st);
+    if constexpr (D * D * 2 <= 64) { if (wc <= 2) return launch_ho_warp_inst<NLEV, D, 2>(h, st); }
+    if constexpr (D * D * 4 <= 64) { if (wc <= 4) return launch_ho_warp_inst<NLEV, D, 4>(h, st); }
+    return GPSIG_E_UNSUPPORTED;
+}
+
+// (levels, order) pairs with order in [2, levels], levels <= 5
+static int launch_ho_warp(const HoParams& h, cudaStream_t st) {
+    switch (h.nlev * 10 + h.order) {
+        case 22: return launch_ho_warp_wc<2, 2>(h, st);
+        case 32: return launch_ho_warp_wc<3, 2>(h, st);
+        case 33: return launch_ho_warp_wc<3, 3>(h, st);
+        case 42: return launch_ho_warp_wc<4, 2>(h, st);
+        case 43: return launch_ho_warp_wc<4, 3>(h, st);
+        case 44: return launch_ho_warp_wc<4, 4>(h, st);
+        case 52: return launch_ho_warp_wc<5, 2>(h, st);
+        case 53: return launch_ho_warp_wc<5, 3>(h, st);
+        case 54: return launch_ho_warp_wc<5, 4>(h, st);
+        case 55: return launch_ho_warp_wc<5, 5>(h, st);
+    }
+    return GPSIG_E_UNSUPPORTED;
+}
+
 int launch_sigkern_ho(const float* M, int n1, int Lrows, int n2, int ncols, long long si, long long ss, long long sj,
                       int nlev, int order, int difference, int upper_only, int i_off, int j_off, long long ldo,
                       long long lvl_stride, float* out, cudaStream_t st) {
@@ -573,6 +759,11 @@ int launch_sigkern_ho(const float* M, int n1, int Lrows, int n2, int ncols, long
     h.nc = ncols;
     h.i_off = i_off; h.j_off = j_off; h.ldo = ldo;
     h.out = out; h.out_level_stride = lvl_stride;
+    {
+        ProfScope prof(GPSIG_PROF_RECURSION_OTHER, st, (double)n1 * n2);
+        const int rc = launch_ho_warp(h, st);  // warp-per-pair kernel where instantiated
+        if (rc != GPSIG_E_UNSUPPORTED) return rc;
+    }
     const size_t per_pair = (size_t)(nlev > 1 ? nlev - 1 : 1) * order * (ncols > 0 ? ncols : 1) * sizeof(float);
     int ppb = 32;
     while (ppb > 1 && per_pair * ppb > 200 * 1024) ppb >>= 1;

@@ -10,7 +10,7 @@
 //     B row (time step)   : [  x_hi |  x_lo |  x_hi | nx_1 nx_2 nx_3 | 1 1 1 ]       nx = -|x|^2
 // (3d + 6 K-slots, padded to a multiple of 32: one or two 128-byte swizzle atoms), accumulated in fp32 by the MMA:
 // error ~ 3 * 2^-22 * |z| |x| in the exponent.  That is small only when the data sits within a few lengthscales of
-// the centre the coordinates are taken from (the data mean): the prep kernel leaves max |x - c|^2 in a flag word, this
+// the centre the coordinates are taken from (the mean of the tensor points): the prep kernel leaves max |x - c|^2 in a flag word, this
 // kernel returns at once when it exceeds kTcRadius2, and the CUDA-core kernel of tens.cu (anchored differences, good
 // anywhere) returns at once when it does not -- both are launched, no host synchronisation.
 //
@@ -145,151 +145,174 @@ tens_seq_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
 
     if (warp == 8) {
         // ===== producer: TMA + MMA issue, one lane ===================================================================
+        // (plain 32-bit counters and incremental iterators: a single thread runs this loop, every 64-bit division in it
+        //  would cost more than the MMAs of a tile)
         if (lane == 0) {
             tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapZ0); tma_prefetch_desc(&mapZ1);
-            long long ld_idx = 0, mma_idx = 0;      // B tiles loaded / multiplied so far (ring position)
-            long long cnt[2] = {0, 0};              // tiles issued per warp set (TMEM buffer = cnt & 1)
-            int item_no = 0;
+            int ld_stage = 0, mma_stage = 0;
+            uint32_t ld_phase = 0, mma_phase = 0;   // ring phases (flip when the stage index wraps)
+            uint32_t cnt[2] = {0, 0};               // tiles issued per warp set (TMEM buffer = cnt & 1)
+            uint32_t item_no = 0;
+            // tiles of an item in issue order: sequences in pairs (set 0 takes the first of a pair), tiles of both interleaved
+            struct It { int na, tt, s; };
             for (long long item = blockIdx.x; item < nitems; item += gridDim.x, ++item_no) {
                 const int zt = (int)(item / p.nch), ch = (int)(item - (long long)zt * p.nch);
-                const long long n0 = (long long)ch * p.chunk;
-                const long long n1 = n0 + p.chunk < p.n ? n0 + p.chunk : p.n;
-                const long long ntile_item = (n1 - n0) * tiles_per_seq;
+                const int n0 = ch * p.chunk;
+                const int n1 = (long long)n0 + p.chunk < p.n ? n0 + p.chunk : (int)p.n;
+                const int ntile_item = (n1 - n0) * tiles_per_seq;
+                auto advance = [&](It& it) {
+                    const int nsets = it.na + 1 < n1 ? 2 : 1;
+                    if (++it.s == nsets) { it.s = 0; if (++it.tt == tiles_per_seq) { it.tt = 0; it.na += 2; } }
+                };
                 // A tiles of this row tile (the previous item's MMAs must have drained first)
-                if (item_no > 0) mbar_wait(mma_done, (uint32_t)(item_no - 1) & 1u);
+                if (item_no > 0) mbar_wait(mma_done, (item_no - 1) & 1u);
                 mbar_arrive_expect_tx(a_full, 2 * kABytes);
 #pragma unroll
                 for (int a = 0; a < KA; ++a) {
                     tma_load_2d(sA0 + a * kTcRows * 128, &mapZ0, a_full, 32 * a, zt * kTcRows);
                     tma_load_2d(sA1 + a * kTcRows * 128, &mapZ1, a_full, 32 * a, zt * kTcRows);
                 }
-                // tile q of the item: sequences in pairs (set 0 takes the even ones of the chunk), tiles of both interleaved
-                auto tile_of = [&](long long q, int& set, long long& nseq, int& tt) {
-                    const long long per_pair = 2LL * tiles_per_seq;
-                    const long long pi = q / per_pair, r = q - pi * per_pair;
-                    const long long na = n0 + 2 * pi;
-                    if (na + 1 < n1) { set = (int)(r & 1); tt = (int)(r >> 1); nseq = na + set; }
-                    else { set = 0; tt = (int)r; nseq = na; }  // odd tail: one sequence, tiles_per_seq tiles
-                };
-                auto issue_load = [&](long long q) {
-                    int set, tt; long long nseq;
-                    tile_of(q, set, nseq, tt);
-                    const int st = (int)(ld_idx % S);
-                    mbar_wait(b_empty + 8 * st, (uint32_t)((ld_idx / S) & 1) ^ 1u);
-                    mbar_arrive_expect_tx(b_full + 8 * st, kBBytes);
+                It li{n0, 0, 0}, mi{n0, 0, 0};
+                auto issue_load = [&]() {
+                    mbar_wait(b_empty + 8 * ld_stage, ld_phase ^ 1u);
+                    mbar_arrive_expect_tx(b_full + 8 * ld_stage, kBBytes);
+                    const int row0 = (li.na + li.s) * p.Lp + li.tt * kTcNT;
 #pragma unroll
                     for (int a = 0; a < KA; ++a)
-                        tma_load_2d(sB + st * kBBytes + a * kTcNT * 128, &mapX, b_full + 8 * st, 32 * a,
-                                    (int)(nseq * p.Lp + (long long)tt * kTcNT));
-                    ++ld_idx;
+                        tma_load_2d(sB + ld_stage * kBBytes + a * kTcNT * 128, &mapX, b_full + 8 * ld_stage, 32 * a, row0);
+                    if (++ld_stage == S) { ld_stage = 0; ld_phase ^= 1u; }
+                    advance(li);
                 };
-                long long loaded = 0;
-                for (; loaded < ntile_item && loaded < S - 1; ++loaded) issue_load(loaded);
-                mbar_wait(a_full, (uint32_t)item_no & 1u);
-                for (long long q = 0; q < ntile_item; ++q) {
-                    if (loaded < ntile_item) { issue_load(loaded); ++loaded; }
-                    int set, tt; long long nseq;
-                    tile_of(q, set, nseq, tt);
-                    const int st = (int)(mma_idx % S);
-                    const int buf = (int)(cnt[set] & 1);
-                    mbar_wait(t_empty + 8 * (set * 2 + buf), (uint32_t)((cnt[set] >> 1) & 1) ^ 1u);  // epilogue drained the buffer
-                    mbar_wait(b_full + 8 * st, (uint32_t)((mma_idx / S) & 1));                       // the time steps have landed
+                int loaded = 0;
+                for (; loaded < ntile_item && loaded < S - 1; ++loaded) issue_load();
+                mbar_wait(a_full, item_no & 1u);
+                for (int q = 0; q < ntile_item; ++q) {
+                    if (loaded < ntile_item) { issue_load(); ++loaded; }
+                    const int set = mi.s;
+                    const uint32_t buf = cnt[set] & 1u;
+                    mbar_wait(t_empty + 8 * (set * 2 + buf), ((cnt[set] >> 1) & 1u) ^ 1u);  // epilogue drained the buffer
+                    mbar_wait(b_full + 8 * mma_stage, mma_phase);                          // the time steps have landed
                     tc_fence_after();
                     const uint32_t d0 = tmem_base + (uint32_t)((set * 2 + buf) * 128), d1 = d0 + kTcNT;
+                    const uint32_t sBs = sB + mma_stage * kBBytes;
 #pragma unroll
-                    for (int ks = 0; ks < 4 * KA; ++ks) {
-                        const uint32_t off = (uint32_t)(ks >> 2) * 128u;  // atom
-                        const uint64_t bd = tc_smem_desc(sB + st * kBBytes + (ks >> 2) * kTcNT * 128 + (ks & 3) * 32);
-                        tc_mma_tf32(d0, tc_smem_desc(sA0 + off * kTcRows + (ks & 3) * 32), bd, kTcIdesc, ks > 0);
-                    }
+                    for (int ks = 0; ks < 4 * KA; ++ks)
+                        tc_mma_tf32(d0, tc_smem_desc(sA0 + (ks >> 2) * kTcRows * 128 + (ks & 3) * 32),
+                                    tc_smem_desc(sBs + (ks >> 2) * kTcNT * 128 + (ks & 3) * 32), kTcIdesc, ks > 0);
 #pragma unroll
-                    for (int ks = 0; ks < 4 * KA; ++ks) {
-                        const uint32_t off = (uint32_t)(ks >> 2) * 128u;
-                        const uint64_t bd = tc_smem_desc(sB + st * kBBytes + (ks >> 2) * kTcNT * 128 + (ks & 3) * 32);
-                        tc_mma_tf32(d1, tc_smem_desc(sA1 + off * kTcRows + (ks & 3) * 32), bd, kTcIdesc, ks > 0);
-                    }
-                    tc_commit(b_empty + 8 * st);                    // the ring stage is free once these MMAs have read it
+                    for (int ks = 0; ks < 4 * KA; ++ks)
+                        tc_mma_tf32(d1, tc_smem_desc(sA1 + (ks >> 2) * kTcRows * 128 + (ks & 3) * 32),
+                                    tc_smem_desc(sBs + (ks >> 2) * kTcNT * 128 + (ks & 3) * 32), kTcIdesc, ks > 0);
+                    tc_commit(b_empty + 8 * mma_stage);             // the ring stage is free once these MMAs have read it
                     tc_commit(t_full + 8 * (set * 2 + buf));        // ... and the accumulators are complete
-                    ++mma_idx;
+                    if (++mma_stage == S) { mma_stage = 0; mma_phase ^= 1u; }
                     ++cnt[set];
+                    advance(mi);
                 }
                 tc_commit(mma_done);
             }
         }
     } else {
         // ===== epilogue: warp set `set`, TMEM lane quarter `quarter` =================================================
+        // The blocks of 16 time steps of all the set's sequences of an item form ONE stream: while the chain rounds of block
+        // g run (long dependent FFMA chains and shared-memory hand-offs), the exponents of block g + 1 are already being
+        // read from TMEM and exponentiated -- the MUFU work hides in the stalls of the rounds.
         const int set = warp >> 2, quarter = warp & 3;
         float* xb = xpatch + warp * 33 * kTcXPitch;
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-        long long cnt = 0;  // tiles consumed by this set
+        uint32_t tile_cnt = 0;  // tiles this set has opened so far (TMEM buffer = tile_cnt & 1)
         const long long per = p.nz * p.n;
+        constexpr int kSB = kTcNT / kTcNB;  // blocks per tile
+        struct Blk { int nseq, tt, sb; uint32_t tile; };
         for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
             const int zt = (int)(item / p.nch), ch = (int)(item - (long long)zt * p.nch);
-            const long long n0 = (long long)ch * p.chunk;
-            const long long n1 = n0 + p.chunk < p.n ? n0 + p.chunk : p.n;
+            const int n0 = ch * p.chunk;
+            const int n1 = (long long)n0 + p.chunk < p.n ? n0 + p.chunk : (int)p.n;
             const TcRow row = p.rows[(long long)zt * kTcRows + quarter * 32 + lane];
             const bool pad = row.m == 0;
             const bool last = !pad && row.p == row.m - 1;
             const int src = (pad || row.p == 0) ? 32 : lane - 1;  // whose prefix this lane multiplies by (32 = the ones row)
-            for (long long nseq = n0 + set; nseq < n1; nseq += 2) {
-                float carry = 0.f, vprev = 0.f;
-                for (int tt = 0; tt < tiles_per_seq; ++tt, ++cnt) {
-                    const int buf = (int)(cnt & 1);
-                    mbar_wait(t_full + 8 * (set * 2 + buf), (uint32_t)((cnt >> 1) & 1));
+            float a0[kTcNB], a1[kTcNB], h[kTcNB], hn[kTcNB];
+            float vprev = 0.f, carry = 0.f;
+            auto advance = [&](Blk& b) {
+                if (++b.sb == kSB) { b.sb = 0; ++b.tile; if (++b.tt == tiles_per_seq) { b.tt = 0; b.nseq += 2; } }
+            };
+            // issue the TMEM loads of block b (waiting for its tile first when it opens one)
+            auto fetch = [&](const Blk& b) {
+                const uint32_t buf = b.tile & 1u;
+                if (b.sb == 0) {
+                    mbar_wait(t_full + 8 * (set * 2 + buf), (b.tile >> 1) & 1u);
                     tc_fence_after();
-                    const uint32_t d0 = tmem_base + lane_base + (uint32_t)((set * 2 + buf) * 128);
-#pragma unroll 1
-                    for (int sb = 0; sb < kTcNT / kTcNB; ++sb) {
-                        float a0[kTcNB], a1[kTcNB], h[kTcNB];
-                        tc_ld16(d0 + sb * kTcNB, a0);
-                        tc_ld16(d0 + kTcNT + sb * kTcNB, a1);
-                        tc_wait_ld();
-#pragma unroll
-                        for (int t = 0; t < kTcNB; ++t) {
-                            const float v = tc_ex2(a1[t]) - tc_ex2(a0[t]);      // kernels.py:330
-                            if (tt == 0 && sb == 0 && t == 0) vprev = v;          // first time step: no increment yet
-                            h[t] = pad ? 0.f : v - vprev;                        // signature_algs.py:114
-                            vprev = v;
-                        }
-                        // NLEV rounds: after round j the lanes at chain position <= j hold their final r
-                        float cin[kTcNB], c[kTcNB];
-#pragma unroll
-                        for (int t = 0; t < kTcNB; ++t) cin[t] = 1.f;
-                        float run = carry;
-#pragma unroll
-                        for (int j = 0; j < NLEV; ++j) {
-                            run = carry;
-#pragma unroll
-                            for (int t = 0; t < kTcNB; ++t) {
-                                c[t] = run;                                      // exclusive prefix (signature_algs.py:123)
-                                run = fmaf(h[t], cin[t], run);
-                            }
-                            if (j + 1 < NLEV) {
-                                float4* w4 = reinterpret_cast<float4*>(xb + lane * kTcXPitch);
-#pragma unroll
-                                for (int t4 = 0; t4 < kTcNB / 4; ++t4) w4[t4] = make_float4(c[4 * t4], c[4 * t4 + 1], c[4 * t4 + 2], c[4 * t4 + 3]);
-                                __syncwarp();
-                                const float4* r4 = reinterpret_cast<const float4*>(xb + src * kTcXPitch);
-#pragma unroll
-                                for (int t4 = 0; t4 < kTcNB / 4; ++t4) {
-                                    const float4 q4 = r4[t4];
-                                    cin[4 * t4] = q4.x; cin[4 * t4 + 1] = q4.y; cin[4 * t4 + 2] = q4.z; cin[4 * t4 + 3] = q4.w;
-                                }
-                                __syncwarp();
-                            }
-                        }
-                        carry = run;
-                    }
+                }
+                const uint32_t d0 = tmem_base + lane_base + (uint32_t)((set * 2 + buf) * 128) + b.sb * kTcNB;
+                tc_ld16(d0, a0);
+                tc_ld16(d0 + kTcNT, a1);
+            };
+            // ... and turn them into the increments h of block b (releasing the TMEM buffer after the last block of a tile)
+            auto finish = [&](const Blk& b, float (&out_h)[kTcNB]) {
+                tc_wait_ld();
+                if (b.sb == kSB - 1) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(t_empty + 8 * (set * 2 + buf));
+                    if (lane == 0) mbar_arrive(t_empty + 8 * (set * 2 + (b.tile & 1u)));
                 }
-                if (last) {
-                    const long long idx = (long long)row.z * p.n + nseq;
+                const bool first_block = b.tt == 0 && b.sb == 0;
+#pragma unroll
+                for (int t = 0; t < kTcNB; ++t) {
+                    const float v = tc_ex2(a1[t]) - tc_ex2(a0[t]);              // kernels.py:330
+                    if (t == 0 && first_block) vprev = v;                        // first time step of a sequence: no increment yet
+                    out_h[t] = pad ? 0.f : v - vprev;                            // signature_algs.py:114
+                    vprev = v;
+                }
+            };
+            Blk cur{n0 + set, 0, 0, tile_cnt}, nxt = cur;
+            if (cur.nseq < n1) { fetch(cur); finish(cur, h); }
+            while (cur.nseq < n1) {
+                nxt = cur;
+                advance(nxt);
+                const bool more = nxt.nseq < n1;
+                if (more) fetch(nxt);
+                if (cur.tt == 0 && cur.sb == 0) carry = 0.f;
+                // NLEV rounds: after round j the lanes at chain position <= j hold their final r
+                float cin[kTcNB], c[kTcNB];
+#pragma unroll
+                for (int t = 0; t < kTcNB; ++t) cin[t] = 1.f;
+                float run = carry;
+#pragma unroll
+                for (int j = 0; j < NLEV; ++j) {
+                    run = carry;
+#pragma unroll
+                    for (int t = 0; t < kTcNB; ++t) {
+                        c[t] = run;                                              // exclusive prefix (signature_algs.py:123)
+                        run = fmaf(h[t], cin[t], run);
+                    }
+                    if (j + 1 < NLEV) {
+                        float4* w4 = reinterpret_cast<float4*>(xb + lane * kTcXPitch);
+#pragma unroll
+                        for (int t4 = 0; t4 < kTcNB / 4; ++t4) w4[t4] = make_float4(c[4 * t4], c[4 * t4 + 1], c[4 * t4 + 2], c[4 * t4 + 3]);
+                        __syncwarp();
+                        if (j == 0 && more) finish(nxt, hn);                     // the next block's MUFU work, off the critical path
+                        const float4* r4 = reinterpret_cast<const float4*>(xb + src * kTcXPitch);
+#pragma unroll
+                        for (int t4 = 0; t4 < kTcNB / 4; ++t4) {
+                            const float4 q4 = r4[t4];
+                            cin[4 * t4] = q4.x; cin[4 * t4 + 1] = q4.y; cin[4 * t4 + 2] = q4.z; cin[4 * t4 + 3] = q4.w;
+                        }
+                        __syncwarp();
+                    }
+                }
+                if (NLEV == 1 && more) finish(nxt, hn);
+                carry = run;
+                if (cur.tt == tiles_per_seq - 1 && cur.sb == kSB - 1 && last) {  // end of a sequence
+                    const long long idx = (long long)row.z * p.n + cur.nseq;
                     p.out[(long long)row.m * per + idx] = carry;               // signature_algs.py:125
                     if (row.m == 1) p.out[idx] = 1.f;
                 }
+#pragma unroll
+                for (int t = 0; t < kTcNB; ++t) h[t] = hn[t];
+                cur = nxt;
             }
+            tile_cnt = cur.tile;
         }
     }
     tc_fence_before();
@@ -313,23 +336,30 @@ __device__ __forceinline__ void tf32_split3(float v, float& p1, float& p2, float
     p3 = tf32_rn(r - p2);
 }
 
-// column sums of the scaled points (for the centre): sums[c] += sum over rows of X[r, c] * inv_ls[c]
-__global__ void tc_centre_kernel(const float* __restrict__ X, long long rows, int d, const float* __restrict__ inv_ls,
-                                 float* __restrict__ sums) {
+// column sums of the scaled points (for the centre): sums[c] = sum over rows of X[r, c] * inv_ls[c].  ONE block, fixed
+// summation order: the centre must be bit-identical from call to call (sharded == single-GPU, reproducible runs)
+__global__ void __launch_bounds__(256) tc_centre_kernel(const float* __restrict__ X, long long rows, int d,
+                                                         const float* __restrict__ inv_ls, float* __restrict__ sums) {
+    __shared__ float part[256];
     for (int c = 0; c < d; ++c) {
         float acc = 0.f;
-        for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x)
-            acc += X[r * d + c] * (inv_ls ? inv_ls[c] : 1.f);
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if ((threadIdx.x & 31) == 0) atomicAdd(sums + c, acc);
+        for (long long r = threadIdx.x; r < rows; r += 256) acc += X[r * d + c] * (inv_ls ? inv_ls[c] : 1.f);
+        part[threadIdx.x] = acc;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) sums[c] = part[0];
+        __syncthreads();
     }
 }
 
 // B operand: one row per (sequence, padded time step); rows past the end of a sequence repeat its last point
 __global__ void tc_prep_x_kernel(const float* __restrict__ X, long long n, int L, int Lp, int d, const float* __restrict__ inv_ls,
-                                 const float* __restrict__ sums, int KW, float* __restrict__ out, unsigned* __restrict__ flag) {
+                                 const float* __restrict__ sums, float inv_rows, int KW, float* __restrict__ out,
+                                 unsigned* __restrict__ flag) {
     const float rs = 0.8493218002880191f;  // sqrt(log2(e) / 2): log2 k = -|x' - z'|^2
-    const float inv_rows = 1.f / (float)(n * L);
     float worst = 0.f;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n * Lp; idx += (long long)gridDim.x * blockDim.x) {
         const long long seq = idx / Lp;
@@ -467,15 +497,19 @@ int launch_tens_seq_tc(const float* Z, long long nz, const float* X, long long n
     // cudaMemcpyAsync from pageable memory returns after the source has been staged, so `rows` may go out of scope
     const int cap = num_sms() * 8;
     {
-        const long long rowsX = n * L;
-        long long blocks = (rowsX + 255) / 256;
-        tc_centre_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(X, rowsX, d, inv_ls, sums);
+        // the centre: the mean of the inducing-tensor points -- the same for every shard of the sequence axis (parallel.py),
+        // so sharded and single-GPU results agree bit for bit; tensors sit where the data sits (gpsig/utils.py:25-63), and if
+        // they do not the flag sends the call to the CUDA-core kernel
+        const int T = nlev * (nlev + 1) / 2;
+        const long long zpts = (long long)T * nz * 2;
+        tc_centre_kernel<<<1, 256, 0, st>>>(Z, zpts, d, inv_ls, sums);
         if ((rc = check_launch())) return done(rc);
-        blocks = (n * Lp + 255) / 256;
-        tc_prep_x_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(X, n, L, Lp, d, inv_ls, sums, KW, Xop, flag);
+        long long blocks = (n * Lp + 255) / 256;
+        tc_prep_x_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(X, n, L, Lp, d, inv_ls, sums, 1.f / (float)zpts, KW, Xop,
+                                                                             flag);
         if ((rc = check_launch())) return done(rc);
         blocks = (2 * nrows + 255) / 256;
-        tc_prep_z_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(Z, nz, d, inv_ls, sums, 1.f / (float)rowsX, drows, nrows,
+        tc_prep_z_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(Z, nz, d, inv_ls, sums, 1.f / (float)zpts, drows, nrows,
                                                                              KW, Z0, Z1);
         if ((rc = check_launch())) return done(rc);
     }

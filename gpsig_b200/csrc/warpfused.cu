@@ -302,6 +302,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_warpfused_kernel(const W
                 for (int i = 0; i < NAP; ++i) AP[i][j] = make_float2(0.f, 0.f);
             }
         }
+        if (EV) __syncwarp();  // the event blocks above are divergent: reconverge before the shuffles
         // running row prefixes arrive from the strip to the left (it finished this row one step ago)
 #pragma unroll
         for (int m = 0; m < NLEV; ++m) {
@@ -340,35 +341,44 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_warpfused_kernel(const W
             for (int h = 1; h < H; ++h) ww = __ffma2_rn(x[h], x[h], ww);
             nw = ww.x + ww.y;
         }
-        auto eval = [&](int u) -> float {  // Gram value (RBF) / increment (LINEAR) of column u of this row
-            if (MODE == 0) {
-                float2 acc = __fmul2_rn(x[0], y[u][0]);
+        // Gram values (RBF) / increments (LINEAR) of the 8 columns of this row, four dot products in flight at a time: the
+        // accumulator chains of a column are dependent FFMA2s, interleaving four of them is what keeps the pipe fed with
+        // three warps per scheduler
+        float f[W];
 #pragma unroll
-                for (int h = 1; h < H; ++h) acc = __ffma2_rn(x[h], y[u][h], acc);
-                return acc.x + acc.y;
-            } else if (MODE == 1) {
-                if (u == kWfAnchor) return wf_ex2(-nw);
-                float2 acc = make_float2(nu[u] - nw, 0.f);
+        for (int half = 0; half < W / 4; ++half) {
+            float2 acc[4];
 #pragma unroll
-                for (int h = 0; h < H; ++h) acc = __ffma2_rn(x[h], y[u][h], acc);
-                return wf_ex2(acc.x + acc.y);
-            } else {
-                float2 df = __fadd2_rn(x[0], y[u][0]);
-                float2 acc = __fmul2_rn(df, df);
-#pragma unroll
-                for (int h = 1; h < H; ++h) {
-                    df = __fadd2_rn(x[h], y[u][h]);
-                    acc = __ffma2_rn(df, df, acc);
-                }
-                return wf_ex2(-(acc.x + acc.y));
+            for (int u4 = 0; u4 < 4; ++u4) {
+                const int u = 4 * half + u4;
+                if (MODE == 0) acc[u4] = __fmul2_rn(x[0], y[u][0]);
+                else if (MODE == 1) acc[u4] = make_float2(nu[u] - nw, 0.f);
+                else { const float2 df = __fadd2_rn(x[0], y[u][0]); acc[u4] = __fmul2_rn(df, df); }
             }
-        };
+#pragma unroll
+            for (int h = (MODE == 1 ? 0 : 1); h < H; ++h)
+#pragma unroll
+                for (int u4 = 0; u4 < 4; ++u4) {
+                    const int u = 4 * half + u4;
+                    if (MODE == 1 && u == kWfAnchor) continue;
+                    if (MODE == 2) { const float2 df = __fadd2_rn(x[h], y[u][h]); acc[u4] = __ffma2_rn(df, df, acc[u4]); }
+                    else acc[u4] = __ffma2_rn(x[h], y[u][h], acc[u4]);
+                }
+#pragma unroll
+            for (int u4 = 0; u4 < 4; ++u4) {
+                const int u = 4 * half + u4;
+                const float v = acc[u4].x + acc[u4].y;
+                if (MODE == 0) f[u] = v;
+                else if (MODE == 1) f[u] = u == kWfAnchor ? wf_ex2(-nw) : wf_ex2(v);
+                else f[u] = wf_ex2(-v);
+            }
+        }
         float fcol = fl;     // RBF: value of the column to the left (lane l owns the increment columns 8 l - 1 .. 8 l + 6; the
                              // value left of its first point belongs to lane l - 1, which evaluated this row one step ago)
         const bool live = valid && (!RBF || !EV || s > 0);  // RBF: the first row of an item only primes the differencing
 #pragma unroll
         for (int up = 0; up < W / 2; ++up) {
-            const float f0 = eval(2 * up), f1 = eval(2 * up + 1);
+            const float f0 = f[2 * up], f1 = f[2 * up + 1];
             float2 dd;
             if (RBF) {
                 const float2 g = make_float2(f0 - fcol, f1 - f0);

@@ -11,7 +11,7 @@ import torch
 
 import cases
 from oracle import gpsig_oracle as O
-from util import GOLDEN, assert_levels_close
+from util import GOLDEN, assert_close, assert_levels_close
 
 pytestmark = pytest.mark.gpu
 
@@ -142,3 +142,35 @@ def test_tens_vs_seq_vs_oracle(nlev, order, nz, n, L, diff):
         ref = O.signature_kern_tens_vs_seq_higher_order(M, nlev, order=order, difference=diff)
         got = S.signature_kern_tens_vs_seq_higher_order(_dev(M), nlev, order=order, difference=diff)
     assert_levels_close(got.cpu().numpy(), ref, msg="tvs")
+
+
+def test_notebook_check_order_M_linear_vs_true_signatures_at_notebook_size():
+    """notebooks/signature_kernel.ipynb:52-55, :117-118, :138-140 at the notebook's own size: N=100, L=50, d=3, M=5,
+    SignatureLinear(order=M, normalization=False).compute_K_symm against inner products of the true truncated signatures
+    (Chen-identity routine instead of esig).  The notebook reports 2e-8 relative in fp64; fp32 here."""
+    from gpsig_b200 import kernels
+    rng = np.random.default_rng(7)
+    n, L, d, Mlev = 100, 50, 3, 5
+    X = rng.standard_normal((n, L, d)) / np.sqrt(L)          # unit-scale paths (randn points as in the notebook, rescaled)
+    sigs = np.stack([O.chen_signature(x, Mlev) for x in X])
+    K_true = sigs @ sigs.T
+    k = kernels.SignatureLinear(L * d, d, Mlev, order=Mlev, normalization=False, lengthscales=None)
+    K = k.compute_K_symm(X.reshape(n, -1))
+    assert_close(K, K_true, tol=1e-4, msg="order=M vs signatures")
+    lv = k.K(X.reshape(n, -1), return_levels=True).cpu().numpy()
+    off = 0
+    for m in range(Mlev + 1):                                  # level by level: <S_m(x), S_m(y)>
+        w = d ** m
+        assert_close(lv[m], sigs[:, off:off + w] @ sigs[:, off:off + w].T, tol=1e-4, msg="level %d" % m)
+        off += w
+
+
+@pytest.mark.parametrize("nlev,order,L", [(4, 4, 64), (5, 5, 50), (5, 3, 128), (3, 2, 20), (5, 4, 100)])
+def test_higher_order_warp_kernel_shapes(nlev, order, L):
+    """the warp-per-pair higher-order kernel (all instantiated grids / strip widths) and the serial fallback (5, 4, 100)"""
+    from gpsig_b200 import signature_algs as S
+    M = _gram(3, L, 4, L, 3, seed=nlev * 100 + order)
+    for diff in (True, False):
+        ref = O.signature_kern_higher_order(M, nlev, order=order, difference=diff)
+        got = S.signature_kern_higher_order(_dev(M), nlev, order=order, difference=diff).cpu().numpy()
+        assert_levels_close(got, ref, msg="ho warp diff=%s" % diff)

@@ -1,0 +1,37 @@
+#!/bin/bash
+TAG=${1:-r2n}
+timeout 120 python tools/debug_tc.py > gpurun_out/${TAG}_tc.log 2>&1; echo "debug_tc rc=$?"; tail -5 gpurun_out/${TAG}_tc.log | cut -c1-250
+timeout 1800 python -m pytest tests -m gpu -q > gpurun_out/${TAG}_gputests_full.log 2>&1
+grep -E "AssertionError: |Error|passed|failed" gpurun_out/${TAG}_gputests_full.log | sort | uniq -c | sort -rn | head -20
+run() {
+  timeout 900 env $3 python bench.py --steps 5 --warmup 3 $2 > gpurun_out/${TAG}_$1.json 2> gpurun_out/${TAG}_$1.err
+  python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/${TAG}_$1.json").read().strip().splitlines()[-1])
+    print("$1", "value %.3e e2e %.3e ms %.3f"%(d["value"], d["e2e"]["value"], d["ms_per_step"]), "fused", round(d["stages"]["fused"]["ms_per_step"],2), "tens", round(d["stages"]["tens"]["ms_per_step"],3), "frac", round(d["roofline"]["frac"],3), "pipe", (d.get("pipeline") or {}).get("ms_per_step"), "cpu", (d.get("cpu_baseline") or {}).get("value"), "parity", {k:(v if not isinstance(v,dict) else v.get("max_abs_err_over_max_abs_ref")) for k,v in d["parity"].items()})
+except Exception as e:
+    print("$1 FAILED", e); print(open("gpurun_out/${TAG}_$1.err").read()[-1500:])
+PY
+}
+run cfg4 "" ""
+run cfg4_linear "--kernel linear --no-cpu-baseline --no-pipeline" ""
+run cfg3 "--workload cfg3 --no-cpu-baseline" ""
+run cfg5 "--workload cfg5 --no-cpu-baseline" ""
+run cfg2 "--workload cfg2 --no-cpu-baseline" ""
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:tens_seq_tc -s 2 -c 1 -f -o gpurun_out/${TAG}_prof_tc python bench.py --workload cfg3 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_ncu_tc.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:sigkern_warpfused -s 2 -c 1 -f -o gpurun_out/${TAG}_prof_wf_rbf python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-pipeline > gpurun_out/${TAG}_ncu_wf_rbf.log 2>&1
+python - <<'PY'
+import time, numpy as np, torch, sys
+sys.path.insert(0, '.')
+import bench
+from gpsig_b200 import kernels
+N, L, d, M = 1024, 64, 6, 4
+X = torch.as_tensor(bench.synth_X(N, L, d).astype(np.float32), device="cuda")
+k = kernels.SignatureLinear(L * d, d, M, order=M, normalization=False)
+for _ in range(2): K = k.K(X)
+torch.cuda.synchronize(); t0 = time.time()
+for _ in range(3): K = k.K(X)
+torch.cuda.synchronize(); dt = (time.time() - t0) / 3
+print("higher-order K(X,X) N=%d L=%d d=%d M=%d order=%d: %.1f ms/step = %.3e pairs/s" % (N, L, d, M, M, dt * 1e3, N * N / dt))
+PY
