@@ -20,11 +20,15 @@
 //   * warp 8, one elected lane: TMA loads (A tiles once per item, B tiles of 64 time steps through a ring) and the MMAs --
 //     per tile 2 x (K/8) tcgen05.mma (M=128, N=64): D0 = exponents against the z^0 points, D1 against the z^1 points,
 //     side by side in TMEM (128 columns per buffer, 2 buffers for each of the 2 warp sets = all 512 columns).
-//   * warps 0-7: two sets of 4 (one warp per TMEM lane quarter); set s takes the sequences n = s (mod 2) of the chunk.  Per
-//     16 time steps a thread reads its row's 2 x 16 exponents (tcgen05.ld 32x32b.x16), v = 2^D1 - 2^D0, h = time
-//     increment of v, then NLEV rounds of (r = h * c_in, running exclusive prefix c, hand c to the next lane of the chain
-//     through a per-warp shared-memory patch).  The prefix carries over tiles; at the end of a sequence the last lane of
-//     each chain owns K_m(z, x_n).
+//   * warps 0-7: two sets of 4 (one warp per TMEM lane quarter); set s takes the sequences n = s (mod 2) of the chunk.  The
+//     blocks of NB time steps of a set's sequences form one stream.  At step b every thread reads its row's 2 x NB
+//     exponents of block b (tcgen05.ld 32x32b), v = 2^D1 - 2^D0, h = time increment of v, and parks h in a per-warp
+//     shared-memory FIFO.  The chain runs SKEWED: the lane at chain position p works on block b - 1 - p (its h from the
+//     FIFO, the exclusive prefix c_in of its predecessor from a double-buffered patch the predecessor filled one step
+//     earlier): r = h * c_in, running prefix, hand the prefix on.  One round per block instead of one per level, and the
+//     chain never waits for the exponentials of the same step.  TMEM addressing is warp-uniform in the column, which is
+//     why the skew lives in shared memory.  The prefix carries over tiles; at the end of a sequence the last lane of each
+//     chain owns K_m(z, x_n).
 // MUFU.EX2 is the bound by design (2 per Gram entry; everything else is ~7 issue slots per entry).
 #include <vector>
 
@@ -34,8 +38,6 @@ namespace gpsig {
 
 constexpr int kTcRows = 128;     // rows (TMEM lanes) per tile
 constexpr int kTcNT = 64;        // time steps per MMA tile
-constexpr int kTcNB = 16;        // time steps per epilogue block
-constexpr int kTcXPitch = 20;    // floats per lane row of the exchange patch (16 + pad: conflict-free 16-byte accesses)
 
 struct TcRow { int z, m, p, k; };  // tensor, level (0 = padding row), position in the chain, component index
 
@@ -70,7 +72,7 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+__device__ __forceinline__ void tc_ld(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -80,6 +82,15 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
         : "memory");
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_ld(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float tc_ex2(float x) {
@@ -99,8 +110,9 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr) {
 constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcNT >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
 
 // ---- the kernel ----------------------------------------------------------------------------------------------------
-// KA = 128-byte K atoms per operand row (1: K = 32 slots, d <= 8;  2: K = 64, d <= 19);  S = stages of the B ring
-template <int NLEV, int KA, int S>
+// KA = 128-byte K atoms per operand row (1: K = 32 slots, d <= 8;  2: K = 64, d <= 19);  S = stages of the B ring;
+// NB = time steps per epilogue block (16, or 8 where shared memory is short)
+template <int NLEV, int KA, int S, int NB>
 __global__ void __launch_bounds__(288, 1)
 tens_seq_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapZ0,
                    const __grid_constant__ CUtensorMap mapZ1, const TcParams p) {
@@ -112,8 +124,12 @@ tens_seq_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
     uint8_t* tsm = tsm_raw + ((1024u - (smem_u32(tsm_raw) & 1023u)) & 1023u);
     const uint32_t smem0 = smem_u32(tsm);
     const uint32_t sA0 = smem0, sA1 = sA0 + kABytes, sB = sA1 + kABytes;
+    // per epilogue warp: FIFO of h blocks [F][32 lanes][NB] and the prefix patch [2][33 rows][NB] (row 32 = ones); 16-byte
+    // chunks of a lane row are XOR-swizzled with the lane index, which makes the per-lane 16-byte accesses conflict free
+    constexpr int F = NLEV + 1;
+    constexpr uint32_t kWarpFloats = (F * 32 + 2 * 33) * NB;
     float* xpatch = reinterpret_cast<float*>(tsm + 2 * kABytes + S * kBBytes);
-    constexpr uint32_t kPatchBytes = 8 * 33 * kTcXPitch * 4;
+    constexpr uint32_t kPatchBytes = 8 * kWarpFloats * 4;
     const uint32_t bars = smem0 + 2 * kABytes + S * kBBytes + kPatchBytes;
     const uint32_t b_full = bars, b_empty = bars + 8 * S, t_full = bars + 16 * S, t_empty = t_full + 32, a_full = t_empty + 32,
                    mma_done = a_full + 8;
@@ -131,9 +147,9 @@ tens_seq_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (warp < 8) {  // the "ones" row of the warp's exchange patch: what the first lane of a chain multiplies by
-        float* xb = xpatch + warp * 33 * kTcXPitch;
-        if (lane < kTcNB) xb[32 * kTcXPitch + lane] = 1.f;
+    if (warp < 8) {  // the "ones" rows of the warp's prefix patch: what the first lane of a chain multiplies by
+        float* pb = xpatch + warp * kWarpFloats + F * 32 * NB;
+        if (lane < NB) { pb[32 * NB + lane] = 1.f; pb[33 * NB + 32 * NB + lane] = 1.f; }
     }
     tc_fence_before();
     __syncthreads();
@@ -214,15 +230,15 @@ tens_seq_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
         }
     } else {
         // ===== epilogue: warp set `set`, TMEM lane quarter `quarter` =================================================
-        // The blocks of 16 time steps of all the set's sequences of an item form ONE stream: while the chain rounds of block
-        // g run (long dependent FFMA chains and shared-memory hand-offs), the exponents of block g + 1 are already being
-        // read from TMEM and exponentiated -- the MUFU work hides in the stalls of the rounds.
         const int set = warp >> 2, quarter = warp & 3;
-        float* xb = xpatch + warp * 33 * kTcXPitch;
+        float* fifo = xpatch + warp * kWarpFloats;     // [F][32][NB]
+        float* patch = fifo + F * 32 * NB;             // [2][33][NB]
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
         uint32_t tile_cnt = 0;  // tiles this set has opened so far (TMEM buffer = tile_cnt & 1)
         const long long per = p.nz * p.n;
-        constexpr int kSB = kTcNT / kTcNB;  // blocks per tile
+        constexpr int kSB = kTcNT / NB;  // blocks per tile
+        constexpr int C4 = NB / 4;       // 16-byte chunks per lane row
+        const int swz = (lane >> 1) & (C4 - 1);
         struct Blk { int nseq, tt, sb; uint32_t tile; };
         for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
             const int zt = (int)(item / p.nch), ch = (int)(item - (long long)zt * p.nch);
@@ -231,9 +247,14 @@ tens_seq_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
             const TcRow row = p.rows[(long long)zt * kTcRows + quarter * 32 + lane];
             const bool pad = row.m == 0;
             const bool last = !pad && row.p == row.m - 1;
-            const int src = (pad || row.p == 0) ? 32 : lane - 1;  // whose prefix this lane multiplies by (32 = the ones row)
-            float a0[kTcNB], a1[kTcNB], h[kTcNB], hn[kTcNB];
+            const int lag = pad ? 1 : row.p + 1;                   // this lane works on block (step - lag)
+            const int src = (pad || row.p == 0) ? 32 : lane - 1;    // whose prefix it multiplies by (32 = the ones row)
+            const int src_swz = src == 32 ? 0 : ((src >> 1) & (C4 - 1));
+            const int nseq_set = n0 + set < n1 ? (n1 - n0 - set + 1) / 2 : 0;
+            const int per_seq = tiles_per_seq * kSB;
+            float a0[NB], a1[NB];
             float vprev = 0.f, carry = 0.f;
+            int bis = -lag, sq = 0;    // block within the sequence / sequence ordinal of THIS lane's (lagged) block
             auto advance = [&](Blk& b) {
                 if (++b.sb == kSB) { b.sb = 0; ++b.tile; if (++b.tt == tiles_per_seq) { b.tt = 0; b.nseq += 2; } }
             };
@@ -244,73 +265,80 @@ tens_seq_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
                     mbar_wait(t_full + 8 * (set * 2 + buf), (b.tile >> 1) & 1u);
                     tc_fence_after();
                 }
-                const uint32_t d0 = tmem_base + lane_base + (uint32_t)((set * 2 + buf) * 128) + b.sb * kTcNB;
-                tc_ld16(d0, a0);
-                tc_ld16(d0 + kTcNT, a1);
+                const uint32_t d0 = tmem_base + lane_base + (uint32_t)((set * 2 + buf) * 128) + b.sb * NB;
+                tc_ld(d0, a0);
+                tc_ld(d0 + kTcNT, a1);
             };
-            // ... and turn them into the increments h of block b (releasing the TMEM buffer after the last block of a tile)
-            auto finish = [&](const Blk& b, float (&out_h)[kTcNB]) {
-                tc_wait_ld();
-                if (b.sb == kSB - 1) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(t_empty + 8 * (set * 2 + (b.tile & 1u)));
-                }
-                const bool first_block = b.tt == 0 && b.sb == 0;
+            Blk cur{n0 + set, 0, 0, tile_cnt};
+            bool have = cur.nseq < n1;
+            int drain = NLEV;          // steps after the last block until the deepest chain position has consumed it
+            int wslot = 0, par = 0;    // FIFO slot written this step, patch buffer written this step
+            if (have) fetch(cur);
+            while (have || drain > 0) {
+                // ---- skewed chain, loads first (they only depend on earlier steps, so the chain's FFMAs can interleave with
+                //      the exponentials below): this lane's block is (step - lag) ----
+                const bool active = bis >= 0 && sq < nseq_set;
+                int rslot = wslot - lag;
+                if (rslot < 0) rslot += F;
+                float h[NB], cin[NB], c[NB];
+                {
+                    const float4* h4 = reinterpret_cast<const float4*>(fifo + (rslot * 32 + lane) * NB);
+                    const float4* c4 = reinterpret_cast<const float4*>(patch + ((par ^ 1) * 33 + src) * NB);
 #pragma unroll
-                for (int t = 0; t < kTcNB; ++t) {
-                    const float v = tc_ex2(a1[t]) - tc_ex2(a0[t]);              // kernels.py:330
-                    if (t == 0 && first_block) vprev = v;                        // first time step of a sequence: no increment yet
-                    out_h[t] = pad ? 0.f : v - vprev;                            // signature_algs.py:114
-                    vprev = v;
+                    for (int q = 0; q < C4; ++q) {
+                        const float4 hv = h4[q ^ swz], cv = c4[q ^ src_swz];
+                        h[4 * q] = hv.x; h[4 * q + 1] = hv.y; h[4 * q + 2] = hv.z; h[4 * q + 3] = hv.w;
+                        cin[4 * q] = cv.x; cin[4 * q + 1] = cv.y; cin[4 * q + 2] = cv.z; cin[4 * q + 3] = cv.w;
+                    }
                 }
-            };
-            Blk cur{n0 + set, 0, 0, tile_cnt}, nxt = cur;
-            if (cur.nseq < n1) { fetch(cur); finish(cur, h); }
-            while (cur.nseq < n1) {
-                nxt = cur;
-                advance(nxt);
-                const bool more = nxt.nseq < n1;
-                if (more) fetch(nxt);
-                if (cur.tt == 0 && cur.sb == 0) carry = 0.f;
-                // NLEV rounds: after round j the lanes at chain position <= j hold their final r
-                float cin[kTcNB], c[kTcNB];
+                // ---- (a) uniform: the increments h of the newest block go into the FIFO ----
+                if (have) {
+                    tc_wait_ld();
+                    if (cur.sb == kSB - 1) {   // last block of a tile: the TMEM buffer is free again
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(t_empty + 8 * (set * 2 + (cur.tile & 1u)));
+                    }
+                    const bool first_block = cur.tt == 0 && cur.sb == 0;
+                    float hnew[NB];
 #pragma unroll
-                for (int t = 0; t < kTcNB; ++t) cin[t] = 1.f;
+                    for (int t = 0; t < NB; ++t) {
+                        const float v = tc_ex2(a1[t]) - tc_ex2(a0[t]);          // kernels.py:330
+                        if (t == 0 && first_block) vprev = v;                    // first time step of a sequence: no increment yet
+                        hnew[t] = pad ? 0.f : v - vprev;                        // signature_algs.py:114
+                        vprev = v;
+                    }
+                    float4* w4 = reinterpret_cast<float4*>(fifo + (wslot * 32 + lane) * NB);
+#pragma unroll
+                    for (int c = 0; c < C4; ++c) w4[c ^ swz] = make_float4(hnew[4 * c], hnew[4 * c + 1], hnew[4 * c + 2], hnew[4 * c + 3]);
+                    advance(cur);
+                    have = cur.nseq < n1;
+                    if (have) fetch(cur);      // the next block's TMEM loads fly while the chain below runs
+                } else {
+                    --drain;
+                }
+                if (bis == 0) carry = 0.f;
                 float run = carry;
 #pragma unroll
-                for (int j = 0; j < NLEV; ++j) {
-                    run = carry;
-#pragma unroll
-                    for (int t = 0; t < kTcNB; ++t) {
-                        c[t] = run;                                              // exclusive prefix (signature_algs.py:123)
-                        run = fmaf(h[t], cin[t], run);
-                    }
-                    if (j + 1 < NLEV) {
-                        float4* w4 = reinterpret_cast<float4*>(xb + lane * kTcXPitch);
-#pragma unroll
-                        for (int t4 = 0; t4 < kTcNB / 4; ++t4) w4[t4] = make_float4(c[4 * t4], c[4 * t4 + 1], c[4 * t4 + 2], c[4 * t4 + 3]);
-                        __syncwarp();
-                        if (j == 0 && more) finish(nxt, hn);                     // the next block's MUFU work, off the critical path
-                        const float4* r4 = reinterpret_cast<const float4*>(xb + src * kTcXPitch);
-#pragma unroll
-                        for (int t4 = 0; t4 < kTcNB / 4; ++t4) {
-                            const float4 q4 = r4[t4];
-                            cin[4 * t4] = q4.x; cin[4 * t4 + 1] = q4.y; cin[4 * t4 + 2] = q4.z; cin[4 * t4 + 3] = q4.w;
-                        }
-                        __syncwarp();
-                    }
+                for (int t = 0; t < NB; ++t) {
+                    c[t] = run;                                                  // exclusive prefix (signature_algs.py:123)
+                    run = fmaf(h[t], cin[t], run);
                 }
-                if (NLEV == 1 && more) finish(nxt, hn);
-                carry = run;
-                if (cur.tt == tiles_per_seq - 1 && cur.sb == kSB - 1 && last) {  // end of a sequence
-                    const long long idx = (long long)row.z * p.n + cur.nseq;
+                if (active) carry = run;
+                {
+                    float4* w4 = reinterpret_cast<float4*>(patch + (par * 33 + lane) * NB);
+#pragma unroll
+                    for (int q = 0; q < C4; ++q) w4[q ^ swz] = make_float4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]);
+                }
+                if (active && bis == per_seq - 1 && last) {                      // end of a sequence
+                    const long long idx = (long long)row.z * p.n + (n0 + set + 2 * sq);
                     p.out[(long long)row.m * per + idx] = carry;               // signature_algs.py:125
                     if (row.m == 1) p.out[idx] = 1.f;
                 }
-#pragma unroll
-                for (int t = 0; t < kTcNB; ++t) h[t] = hn[t];
-                cur = nxt;
+                if (++bis == per_seq) { bis = 0; ++sq; }
+                if (++wslot == F) wslot = 0;
+                par ^= 1;
+                __syncwarp();
             }
             tile_cnt = cur.tile;
         }
@@ -440,9 +468,12 @@ bool tens_tc_supported(int kind, int d, int nlev, int order, int increments, int
 
 template <int NLEV, int KA>
 static int launch_tc_inst(const CUtensorMap& mx, const CUtensorMap& mz0, const CUtensorMap& mz1, const TcParams& p, cudaStream_t st) {
-    constexpr int S = KA == 1 ? 6 : 4;
-    auto kern = tens_seq_tc_kernel<NLEV, KA, S>;
-    const size_t smem = 2 * (size_t)KA * kTcRows * 128 + (size_t)S * KA * kTcNT * 128 + 8 * 33 * kTcXPitch * 4 + 16 * S + 80 + 16 + 1024;
+    constexpr int S = KA == 1 ? 4 : 3;
+    constexpr int NB = KA == 1 ? 16 : 8;
+    auto kern = tens_seq_tc_kernel<NLEV, KA, S, NB>;
+    const size_t smem = 2 * (size_t)KA * kTcRows * 128 + (size_t)S * KA * kTcNT * 128 + 8 * (size_t)((NLEV + 1) * 32 + 66) * NB * 4 +
+                        16 * S + 80 + 16 + 1024;
+    if (smem > 232448) return GPSIG_E_UNSUPPORTED;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const long long nitems = (long long)p.ntiles * p.nch;
