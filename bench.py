@@ -296,6 +296,18 @@ def fp32_ops_per_kuf_entry(kind, d):
     return 2 * (d + 2) + 1 + 1 + 2 if kind == "rbf" else d + 2
 
 
+def tcgen05_takes_kuf(kind, Xnp, Znp, ls, d, M, low_rank):
+    """Host-side restatement of the device gate of tens_tc.cu (tens_tc_supported + the radius flag of tc_prep_x_kernel): does
+    the tcgen05 kernel take this Kuf call, or does the CUDA-core kernel of tens.cu?  Only names the roofline; no effect on
+    what runs."""
+    if kind != "rbf" or low_rank or os.environ.get("GPSIG_TENS_TC", "1") == "0" or 3 * d + 6 > 64 or M > 6:
+        return False
+    rs = np.sqrt(np.log2(np.e) / 2.0)
+    c = (Znp.reshape(-1, d).astype(np.float64) / ls).mean(axis=0)
+    r2 = (((Xnp.reshape(-1, d).astype(np.float64) / ls - c) * rs) ** 2).sum(axis=1).max()
+    return bool(r2 <= 16.0)
+
+
 class SharedHostMatrix:
     """One pinned host matrix visible to every rank of the node (file in /dev/shm mapped shared, registered with CUDA):
     each rank copies ITS slab of the result there, so the e2e path needs no second collective."""
@@ -376,11 +388,13 @@ def run_ours(args, wl):
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     units = units_per_step(wl)
     Zd = Zh = model = None
+    tc_path = False
     if wtype in ("kuf", "elbo"):
         nz = wl["Z"]
         Znp = synth_Z(Xnp.astype(np.float64), L, d, M, nz).astype(np.float32)
         Zh = torch.from_numpy(Znp).pin_memory()
         Zd = Zh.to(dev)
+        tc_path = tcgen05_takes_kuf(kind, Xnp, Znp, lengthscales_for(kind, d), d, M, args.low_rank)
     if wtype == "elbo":
         Ynp = (np.arange(N)[:, None] % 2).astype(np.float64)
         rngq = np.random.default_rng(7)
@@ -533,10 +547,29 @@ def run_ours(args, wl):
     else:
         T = M * (M + 1) // 2
         per_pair = fp32_ops_per_kuf_entry(kind, d) * T * L
-        roofline = roof_fp32("tens_seq_fast_kernel", prof["tens"], ms_total, per_pair,
-                             load_traffic("%s_tens_bytes_per_launch" % args.workload) if world == 1 else None,
-                             "(tensor, sequence) pair = T L = %d x %d component-time entries x %d lane-ops"
-                             % (T, L, fp32_ops_per_kuf_entry(kind, d)))
+        traffic = load_traffic("%s_tens_bytes_per_launch" % args.workload) if world == 1 else None
+        fp32_roof = roof_fp32("tens_seq_fast_kernel", prof["tens"], ms_total, per_pair, traffic,
+                              "(tensor, sequence) pair = T L = %d x %d component-time entries x %d lane-ops"
+                              % (T, L, fp32_ops_per_kuf_entry(kind, d)))
+        if tc_path:
+            # the tcgen05 kernel moves the Gram onto the tensor cores; what is left per Gram entry is ONE MUFU.EX2, and the
+            # SFU (16 lanes / clk / SM, tools/ubench/pipes.cu) is the pipe that bounds it: 2 T L exponentials per pair
+            r_ms, r_n, r_units = prof["tens"]
+            ex_per_pair = 2 * T * L
+            peak_mufu = 148 * 16 * sm_hz / 1e12
+            achieved = r_units * ex_per_pair / (r_ms * 1e-3) / 1e12 if r_ms > 0 else 0.0
+            roofline = {"bound": "mufu", "kernel": "tens_seq_tc_kernel", "achieved": achieved, "peak": peak_mufu, "unit": "Tex2/s",
+                        "frac": achieved / peak_mufu, "traffic": traffic,
+                        "peak_source": "148 SMs x 16 SFU lanes x %.0f MHz (MUFU.EX2 measured at 0.5 warp-instr/clk/SM, "
+                                       "profiles/r2a_pipes.log)" % (sm_hz / 1e6),
+                        "ex2_per_unit": ex_per_pair, "unit_of_work": "(tensor, sequence) pair = 2 T L = 2 x %d x %d static-kernel "
+                        "evaluations; their d-term dot products run on tcgen05 (kind::tf32, split operands)" % (T, L),
+                        "units_per_launch": r_units / max(r_n, 1), "launches": r_n, "avg_launch_ms": r_ms / max(r_n, 1),
+                        "kernel_share_of_step": r_ms / ms_total,
+                        "cuda_core_equivalent": dict(fp32_roof, note="the same work counted as the CUDA-core kernel's FP32 lane-ops "
+                                                     "(a fraction above 1 is what moving the Gram to the tensor cores bought)")}
+        else:
+            roofline = fp32_roof
     stages = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in prof.items()}
 
     # parity (not timed): entries of what the timed steps produced against the fp64 oracle
