@@ -134,7 +134,7 @@ constexpr int kWfMaxRowBlocks = 32;
 // 1.5e-7 |u|^2 relative to k)
 constexpr float kWfJumpThreshold = 4.0f;
 bool warpfused_supported(bool rbf, int d, int nlev, int ncols, int rowsA);
-struct WfAnchored { float* Bu; float* Bnu; float* Banc; int nstrip; };  // column side of the anchored RBF form
+struct WfAnchored { float* Bu; float* Bnu; int rows_padded; };  // column side of the anchored RBF form (warpfused.cu)
 size_t wf_anchor_bytes(long long n, int rows, int D);
 int launch_wf_anchor_prep(const float* B, long long n, int rows, int D, void* buf, unsigned* flag, WfAnchored* out,
                           cudaStream_t st);

@@ -423,7 +423,8 @@ static int launch_tsf_fast_inst(const TsfFastParams& p, cudaStream_t st) {
     const size_t smem = (size_t)kTsfZPerBlock * (T * nst * DPA + ((T + 3) & ~3)) * sizeof(float);
     dim3 grid((unsigned)((p.n + 32 * kTsfSeqPerThread - 1) / (32 * kTsfSeqPerThread)),
               (unsigned)((p.nz + kTsfZPerBlock - 1) / kTsfZPerBlock));
-    ProfScope prof(GPSIG_PROF_TENS, st, (double)p.nz * p.n);
+    // units are counted once per call: with a tensor-core launch in front (tens_tc.cu) that launch carries them
+    ProfScope prof(GPSIG_PROF_TENS, st, p.tcflag ? 0.0 : (double)p.nz * p.n);
     auto k = tens_seq_fast_kernel<RBF, NLEV, DPA>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<grid, kTsfZPerBlock * 32, smem, st>>>(p);

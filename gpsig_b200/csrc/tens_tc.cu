@@ -30,6 +30,7 @@
 //     why the skew lives in shared memory.  The prefix carries over tiles; at the end of a sequence the last lane of each
 //     chain owns K_m(z, x_n).
 // MUFU.EX2 is the bound by design (2 per Gram entry; everything else is ~7 issue slots per entry).
+#include <type_traits>
 #include <vector>
 
 #include "internal.cuh"
@@ -38,6 +39,7 @@ namespace gpsig {
 
 constexpr int kTcRows = 128;     // rows (TMEM lanes) per tile
 constexpr int kTcNT = 64;        // time steps per MMA tile
+constexpr int kTcThreads = 320;  // 8 epilogue warps (2 sets x 4 TMEM lane quarters) + 2 producer warps
 
 struct TcRow { int z, m, p, k; };  // tensor, level (0 = padding row), position in the chain, component index
 
@@ -112,15 +114,25 @@ constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(k
 // ---- the kernel ----------------------------------------------------------------------------------------------------
 // KA = 128-byte K atoms per operand row (1: K = 32 slots, d <= 8;  2: K = 64, d <= 19);  S = stages of the B ring;
 // NB = time steps per epilogue block (16, or 8 where shared memory is short)
+// register fence: the values of a completed tcgen05.ld may only be read after tcgen05.wait::ld; the empty volatile asm
+// keeps its place after the (volatile) wait and every use of v depends on it
+template <int N>
+__device__ __forceinline__ void tc_reg_fence(float (&v)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; i += 8)
+        asm volatile("" : "+f"(v[i]), "+f"(v[i + 1]), "+f"(v[i + 2]), "+f"(v[i + 3]), "+f"(v[i + 4]), "+f"(v[i + 5]), "+f"(v[i + 6]),
+                          "+f"(v[i + 7]));
+}
+
 template <int NLEV, int KA, int S, int NB>
-__global__ void __launch_bounds__(288, 1)
+__global__ void __launch_bounds__(kTcThreads, 1)
 tens_seq_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapZ0,
                    const __grid_constant__ CUtensorMap mapZ1, const TcParams p) {
     if (__uint_as_float(*p.flag) > kTcRadius2) return;  // data too spread for the split-TF32 exponent: tens.cu does the call
     extern __shared__ __align__(1024) uint8_t tsm_raw[];
     constexpr uint32_t kABytes = KA * kTcRows * 128, kBBytes = KA * kTcNT * 128;
-    // layout: A0 | A1 | B ring | exchange patches (8 warps x 33 rows) | barriers | tmem base   (1024-byte aligned: the
-    // 128-byte swizzle of TMA and of the MMA descriptors is a function of the absolute shared-memory address)
+    // layout: A0 | A1 | B ring of set 0 | B ring of set 1 | FIFOs and prefix patches of the 8 epilogue warps | barriers | tmem
+    // base   (1024-byte aligned: the 128-byte swizzle of TMA and of the MMA descriptors is a function of the absolute address)
     uint8_t* tsm = tsm_raw + ((1024u - (smem_u32(tsm_raw) & 1023u)) & 1023u);
     const uint32_t smem0 = smem_u32(tsm);
     const uint32_t sA0 = smem0, sA1 = sA0 + kABytes, sB = sA1 + kABytes;
@@ -128,19 +140,21 @@ tens_seq_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
     // chunks of a lane row are XOR-swizzled with the lane index, which makes the per-lane 16-byte accesses conflict free
     constexpr int F = NLEV + 1;
     constexpr uint32_t kWarpFloats = (F * 32 + 2 * 33) * NB;
-    float* xpatch = reinterpret_cast<float*>(tsm + 2 * kABytes + S * kBBytes);
+    float* xpatch = reinterpret_cast<float*>(tsm + 2 * kABytes + 2 * S * kBBytes);
     constexpr uint32_t kPatchBytes = 8 * kWarpFloats * 4;
-    const uint32_t bars = smem0 + 2 * kABytes + S * kBBytes + kPatchBytes;
-    const uint32_t b_full = bars, b_empty = bars + 8 * S, t_full = bars + 16 * S, t_empty = t_full + 32, a_full = t_empty + 32,
+    const uint32_t bars = smem0 + 2 * kABytes + 2 * S * kBBytes + kPatchBytes;
+    // b_full[set][S] | b_empty[set][S] | t_full[4] | t_empty[4] | a_full | mma_done[2]
+    const uint32_t b_full = bars, b_empty = bars + 16 * S, t_full = bars + 32 * S, t_empty = t_full + 32, a_full = t_empty + 32,
                    mma_done = a_full + 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tsm + 2 * kABytes + S * kBBytes + kPatchBytes + 16 * S + 80);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tsm + 2 * kABytes + 2 * S * kBBytes + kPatchBytes + 32 * S + 96);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < S; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
+        for (int i = 0; i < 2 * S; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
         for (int i = 0; i < 4; ++i) { mbar_init(t_full + 8 * i, 1); mbar_init(t_empty + 8 * i, 4); }
         mbar_init(a_full, 1);
         mbar_init(mma_done, 1);
+        mbar_init(mma_done + 8, 1);
         fence_mbar_init();
     }
     if (warp == 8) {  // TMEM: all 512 columns (one CTA per SM)
@@ -159,58 +173,62 @@ tens_seq_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
     const int tiles_per_seq = p.Lp / kTcNT;
     const long long nitems = (long long)p.ntiles * p.nch;
 
-    if (warp == 8) {
-        // ===== producer: TMA + MMA issue, one lane ===================================================================
-        // (plain 32-bit counters and incremental iterators: a single thread runs this loop, every 64-bit division in it
-        //  would cost more than the MMAs of a tile)
+    if (warp >= 8) {
+        // ===== two producers (TMA + MMA issue, one lane each): warp 8 feeds warp set 0, warp 9 feeds set 1.  Each owns a ring
+        // of B stages and the two TMEM buffers of its set, so a set that runs ahead never waits for the other; the A tiles
+        // of an item are shared (loaded by producer 0 once BOTH producers' MMAs of the previous item have drained).
+        // (plain 32-bit counters and incremental iterators: every 64-bit division in this loop would cost more than the
+        //  MMAs of a tile)
+        const int set = warp - 8;
         if (lane == 0) {
-            tma_prefetch_desc(&mapX); tma_prefetch_desc(&mapZ0); tma_prefetch_desc(&mapZ1);
+            tma_prefetch_desc(&mapX);
+            if (set == 0) { tma_prefetch_desc(&mapZ0); tma_prefetch_desc(&mapZ1); }
+            const uint32_t bf = b_full + 8 * S * set, be = b_empty + 8 * S * set, sBr = sB + set * S * kBBytes;
             int ld_stage = 0, mma_stage = 0;
             uint32_t ld_phase = 0, mma_phase = 0;   // ring phases (flip when the stage index wraps)
-            uint32_t cnt[2] = {0, 0};               // tiles issued per warp set (TMEM buffer = cnt & 1)
+            uint32_t cnt = 0;                       // tiles issued for this set (TMEM buffer = cnt & 1)
             uint32_t item_no = 0;
-            // tiles of an item in issue order: sequences in pairs (set 0 takes the first of a pair), tiles of both interleaved
-            struct It { int na, tt, s; };
             for (long long item = blockIdx.x; item < nitems; item += gridDim.x, ++item_no) {
                 const int zt = (int)(item / p.nch), ch = (int)(item - (long long)zt * p.nch);
                 const int n0 = ch * p.chunk;
                 const int n1 = (long long)n0 + p.chunk < p.n ? n0 + p.chunk : (int)p.n;
-                const int ntile_item = (n1 - n0) * tiles_per_seq;
-                auto advance = [&](It& it) {
-                    const int nsets = it.na + 1 < n1 ? 2 : 1;
-                    if (++it.s == nsets) { it.s = 0; if (++it.tt == tiles_per_seq) { it.tt = 0; it.na += 2; } }
-                };
-                // A tiles of this row tile (the previous item's MMAs must have drained first)
-                if (item_no > 0) mbar_wait(mma_done, (item_no - 1) & 1u);
-                mbar_arrive_expect_tx(a_full, 2 * kABytes);
+                const int nseq_set = n0 + set < n1 ? (n1 - n0 - set + 1) / 2 : 0;   // sequences n0 + set, n0 + set + 2, ...
+                const int ntile = nseq_set * tiles_per_seq;
+                if (set == 0) {
+                    if (item_no > 0) {
+                        mbar_wait(mma_done, (item_no - 1) & 1u);
+                        mbar_wait(mma_done + 8, (item_no - 1) & 1u);
+                    }
+                    mbar_arrive_expect_tx(a_full, 2 * kABytes);
 #pragma unroll
-                for (int a = 0; a < KA; ++a) {
-                    tma_load_2d(sA0 + a * kTcRows * 128, &mapZ0, a_full, 32 * a, zt * kTcRows);
-                    tma_load_2d(sA1 + a * kTcRows * 128, &mapZ1, a_full, 32 * a, zt * kTcRows);
+                    for (int a = 0; a < KA; ++a) {
+                        tma_load_2d(sA0 + a * kTcRows * 128, &mapZ0, a_full, 32 * a, zt * kTcRows);
+                        tma_load_2d(sA1 + a * kTcRows * 128, &mapZ1, a_full, 32 * a, zt * kTcRows);
+                    }
                 }
-                It li{n0, 0, 0}, mi{n0, 0, 0};
+                int l_na = n0 + set, l_tt = 0;   // next tile to load
                 auto issue_load = [&]() {
-                    mbar_wait(b_empty + 8 * ld_stage, ld_phase ^ 1u);
-                    mbar_arrive_expect_tx(b_full + 8 * ld_stage, kBBytes);
-                    const int row0 = (li.na + li.s) * p.Lp + li.tt * kTcNT;
+                    mbar_wait(be + 8 * ld_stage, ld_phase ^ 1u);
+                    mbar_arrive_expect_tx(bf + 8 * ld_stage, kBBytes);
+                    const int row0 = l_na * p.Lp + l_tt * kTcNT;
 #pragma unroll
                     for (int a = 0; a < KA; ++a)
-                        tma_load_2d(sB + ld_stage * kBBytes + a * kTcNT * 128, &mapX, b_full + 8 * ld_stage, 32 * a, row0);
+                        tma_load_2d(sBr + ld_stage * kBBytes + a * kTcNT * 128, &mapX, bf + 8 * ld_stage, 32 * a, row0);
                     if (++ld_stage == S) { ld_stage = 0; ld_phase ^= 1u; }
-                    advance(li);
+                    if (++l_tt == tiles_per_seq) { l_tt = 0; l_na += 2; }
                 };
                 int loaded = 0;
-                for (; loaded < ntile_item && loaded < S - 1; ++loaded) issue_load();
-                mbar_wait(a_full, item_no & 1u);
-                for (int q = 0; q < ntile_item; ++q) {
-                    if (loaded < ntile_item) { issue_load(); ++loaded; }
-                    const int set = mi.s;
-                    const uint32_t buf = cnt[set] & 1u;
-                    mbar_wait(t_empty + 8 * (set * 2 + buf), ((cnt[set] >> 1) & 1u) ^ 1u);  // epilogue drained the buffer
-                    mbar_wait(b_full + 8 * mma_stage, mma_phase);                          // the time steps have landed
+                for (; loaded < ntile && loaded < S - 1; ++loaded) issue_load();
+                if (ntile > 0) mbar_wait(a_full, item_no & 1u);
+                for (int q = 0; q < ntile; ++q) {
+                    if (loaded < ntile) { issue_load(); ++loaded; }
+                    const uint32_t buf = cnt & 1u;
+                    // the epilogue has drained the buffer (two tiles of slack: back off instead of spinning on the issue port)
+                    while (!mbar_try_wait(t_empty + 8 * (set * 2 + buf), ((cnt >> 1) & 1u) ^ 1u)) __nanosleep(256);
+                    mbar_wait(bf + 8 * mma_stage, mma_phase);                          // the time steps have landed
                     tc_fence_after();
                     const uint32_t d0 = tmem_base + (uint32_t)((set * 2 + buf) * 128), d1 = d0 + kTcNT;
-                    const uint32_t sBs = sB + mma_stage * kBBytes;
+                    const uint32_t sBs = sBr + mma_stage * kBBytes;
 #pragma unroll
                     for (int ks = 0; ks < 4 * KA; ++ks)
                         tc_mma_tf32(d0, tc_smem_desc(sA0 + (ks >> 2) * kTcRows * 128 + (ks & 3) * 32),
@@ -219,13 +237,13 @@ tens_seq_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
                     for (int ks = 0; ks < 4 * KA; ++ks)
                         tc_mma_tf32(d1, tc_smem_desc(sA1 + (ks >> 2) * kTcRows * 128 + (ks & 3) * 32),
                                     tc_smem_desc(sBs + (ks >> 2) * kTcNT * 128 + (ks & 3) * 32), kTcIdesc, ks > 0);
-                    tc_commit(b_empty + 8 * mma_stage);             // the ring stage is free once these MMAs have read it
+                    tc_commit(be + 8 * mma_stage);                  // the ring stage is free once these MMAs have read it
                     tc_commit(t_full + 8 * (set * 2 + buf));        // ... and the accumulators are complete
                     if (++mma_stage == S) { mma_stage = 0; mma_phase ^= 1u; }
-                    ++cnt[set];
-                    advance(mi);
+                    ++cnt;
                 }
-                tc_commit(mma_done);
+                if (ntile > 0) tc_commit(mma_done + 8 * set);       // this set's reads of the A tiles are over
+                else mbar_arrive(mma_done + 8 * set);
             }
         }
     } else {
@@ -233,54 +251,47 @@ tens_seq_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
         const int set = warp >> 2, quarter = warp & 3;
         float* fifo = xpatch + warp * kWarpFloats;     // [F][32][NB]
         float* patch = fifo + F * 32 * NB;             // [2][33][NB]
-        const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-        uint32_t tile_cnt = 0;  // tiles this set has opened so far (TMEM buffer = tile_cnt & 1)
+        const uint32_t tmem_set = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(set * 256);
+        uint32_t tile = 0;  // tiles this set has opened so far (TMEM buffer = tile & 1)
         const long long per = p.nz * p.n;
-        constexpr int kSB = kTcNT / NB;  // blocks per tile
+        constexpr int kSB = kTcNT / NB;  // blocks per tile (even: the register buffer of a block is its parity)
         constexpr int C4 = NB / 4;       // 16-byte chunks per lane row
+        static_assert(kSB % 2 == 0 && kSB >= 4, "two register buffers alternate over the blocks of a tile");
         const int swz = (lane >> 1) & (C4 - 1);
-        struct Blk { int nseq, tt, sb; uint32_t tile; };
         for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
             const int zt = (int)(item / p.nch), ch = (int)(item - (long long)zt * p.nch);
             const int n0 = ch * p.chunk;
             const int n1 = (long long)n0 + p.chunk < p.n ? n0 + p.chunk : (int)p.n;
+            const int nseq_set = n0 + set < n1 ? (n1 - n0 - set + 1) / 2 : 0;
+            if (nseq_set == 0) continue;
             const TcRow row = p.rows[(long long)zt * kTcRows + quarter * 32 + lane];
             const bool pad = row.m == 0;
             const bool last = !pad && row.p == row.m - 1;
             const int lag = pad ? 1 : row.p + 1;                   // this lane works on block (step - lag)
             const int src = (pad || row.p == 0) ? 32 : lane - 1;    // whose prefix it multiplies by (32 = the ones row)
             const int src_swz = src == 32 ? 0 : ((src >> 1) & (C4 - 1));
-            const int nseq_set = n0 + set < n1 ? (n1 - n0 - set + 1) / 2 : 0;
             const int per_seq = tiles_per_seq * kSB;
-            float a0[NB], a1[NB];
+            const int tiles_item = nseq_set * tiles_per_seq;
+            float a[2][2][NB];         // [register buffer][z^0 / z^1 accumulator][time step]
             float vprev = 0.f, carry = 0.f;
             int bis = -lag, sq = 0;    // block within the sequence / sequence ordinal of THIS lane's (lagged) block
-            auto advance = [&](Blk& b) {
-                if (++b.sb == kSB) { b.sb = 0; ++b.tile; if (++b.tt == tiles_per_seq) { b.tt = 0; b.nseq += 2; } }
-            };
-            // issue the TMEM loads of block b (waiting for its tile first when it opens one)
-            auto fetch = [&](const Blk& b) {
-                const uint32_t buf = b.tile & 1u;
-                if (b.sb == 0) {
-                    mbar_wait(t_full + 8 * (set * 2 + buf), (b.tile >> 1) & 1u);
-                    tc_fence_after();
-                }
-                const uint32_t d0 = tmem_base + lane_base + (uint32_t)((set * 2 + buf) * 128) + b.sb * NB;
-                tc_ld(d0, a0);
-                tc_ld(d0 + kTcNT, a1);
-            };
-            Blk cur{n0 + set, 0, 0, tile_cnt};
-            bool have = cur.nseq < n1;
-            int drain = NLEV;          // steps after the last block until the deepest chain position has consumed it
             int wslot = 0, par = 0;    // FIFO slot written this step, patch buffer written this step
-            if (have) fetch(cur);
-            while (have || drain > 0) {
-                // ---- skewed chain, loads first (they only depend on earlier steps, so the chain's FFMAs can interleave with
-                //      the exponentials below): this lane's block is (step - lag) ----
+            auto open_tile = [&](uint32_t t) {
+                mbar_wait(t_full + 8 * (set * 2 + (t & 1u)), (t >> 1) & 1u);
+                tc_fence_after();
+            };
+            auto load_block = [&](uint32_t t, int sb, float (&dst)[2][NB]) {
+                const uint32_t d0 = tmem_set + (t & 1u) * 128 + sb * NB;
+                tc_ld(d0, dst[0]);
+                tc_ld(d0 + kTcNT, dst[1]);
+            };
+            // one step of the skewed chain; HAVE: a new block (in registers `blk`) enters the FIFO this step
+            auto step = [&](auto have_c, float (&blk)[2][NB], bool first_block) {
+                constexpr bool HAVE = decltype(have_c)::value;
                 const bool active = bis >= 0 && sq < nseq_set;
                 int rslot = wslot - lag;
                 if (rslot < 0) rslot += F;
-                float h[NB], cin[NB], c[NB];
+                float h[NB], cin[NB];
                 {
                     const float4* h4 = reinterpret_cast<const float4*>(fifo + (rslot * 32 + lane) * NB);
                     const float4* c4 = reinterpret_cast<const float4*>(patch + ((par ^ 1) * 33 + src) * NB);
@@ -291,45 +302,33 @@ tens_seq_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
                         cin[4 * q] = cv.x; cin[4 * q + 1] = cv.y; cin[4 * q + 2] = cv.z; cin[4 * q + 3] = cv.w;
                     }
                 }
-                // ---- (a) uniform: the increments h of the newest block go into the FIFO ----
-                if (have) {
-                    tc_wait_ld();
-                    if (cur.sb == kSB - 1) {   // last block of a tile: the TMEM buffer is free again
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(t_empty + 8 * (set * 2 + (cur.tile & 1u)));
-                    }
-                    const bool first_block = cur.tt == 0 && cur.sb == 0;
+                if constexpr (HAVE) {
+                    // the increments h of the newest block go into the FIFO (padding rows of A are zero rows: both
+                    // accumulators are equal there, so their h is exactly 0)
                     float hnew[NB];
 #pragma unroll
                     for (int t = 0; t < NB; ++t) {
-                        const float v = tc_ex2(a1[t]) - tc_ex2(a0[t]);          // kernels.py:330
-                        if (t == 0 && first_block) vprev = v;                    // first time step of a sequence: no increment yet
-                        hnew[t] = pad ? 0.f : v - vprev;                        // signature_algs.py:114
+                        const float v = tc_ex2(blk[1][t]) - tc_ex2(blk[0][t]);   // kernels.py:330
+                        if (t == 0) vprev = first_block ? v : vprev;            // first time step of a sequence: no increment yet
+                        hnew[t] = v - vprev;                                    // signature_algs.py:114
                         vprev = v;
                     }
                     float4* w4 = reinterpret_cast<float4*>(fifo + (wslot * 32 + lane) * NB);
 #pragma unroll
                     for (int c = 0; c < C4; ++c) w4[c ^ swz] = make_float4(hnew[4 * c], hnew[4 * c + 1], hnew[4 * c + 2], hnew[4 * c + 3]);
-                    advance(cur);
-                    have = cur.nseq < n1;
-                    if (have) fetch(cur);      // the next block's TMEM loads fly while the chain below runs
-                } else {
-                    --drain;
                 }
-                if (bis == 0) carry = 0.f;
-                float run = carry;
+                float run = bis == 0 ? 0.f : carry;
+                float4* w4 = reinterpret_cast<float4*>(patch + (par * 33 + lane) * NB);
 #pragma unroll
-                for (int t = 0; t < NB; ++t) {
-                    c[t] = run;                                                  // exclusive prefix (signature_algs.py:123)
-                    run = fmaf(h[t], cin[t], run);
+                for (int q = 0; q < C4; ++q) {
+                    float4 cv;                                                   // exclusive prefix (signature_algs.py:123)
+                    cv.x = run; run = fmaf(h[4 * q], cin[4 * q], run);
+                    cv.y = run; run = fmaf(h[4 * q + 1], cin[4 * q + 1], run);
+                    cv.z = run; run = fmaf(h[4 * q + 2], cin[4 * q + 2], run);
+                    cv.w = run; run = fmaf(h[4 * q + 3], cin[4 * q + 3], run);
+                    w4[q ^ swz] = cv;
                 }
-                if (active) carry = run;
-                {
-                    float4* w4 = reinterpret_cast<float4*>(patch + (par * 33 + lane) * NB);
-#pragma unroll
-                    for (int q = 0; q < C4; ++q) w4[q ^ swz] = make_float4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]);
-                }
+                carry = active ? run : carry;
                 if (active && bis == per_seq - 1 && last) {                      // end of a sequence
                     const long long idx = (long long)row.z * p.n + (n0 + set + 2 * sq);
                     p.out[(long long)row.m * per + idx] = carry;               // signature_algs.py:125
@@ -339,8 +338,39 @@ tens_seq_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
                 if (++wslot == F) wslot = 0;
                 par ^= 1;
                 __syncwarp();
-            }
-            tile_cnt = cur.tile;
+            };
+            // the first two blocks of the item
+            open_tile(tile);
+            load_block(tile, 0, a[0]);
+            load_block(tile, 1, a[1]);
+            tc_wait_ld();
+            tc_reg_fence(a[0][0]); tc_reg_fence(a[0][1]); tc_reg_fence(a[1][0]); tc_reg_fence(a[1][1]);
+            int tl = 0;   // tile of the item
+            for (int s = 0; s < nseq_set; ++s)
+                for (int tt = 0; tt < tiles_per_seq; ++tt, ++tile, ++tl) {
+#pragma unroll
+                    for (int sb = 0; sb < kSB; ++sb) {
+                        step(std::true_type{}, a[sb & 1], tt == 0 && sb == 0);
+                        // block (sb + 1) -- loaded a step ago -- is complete after this wait; block (sb + 2) takes the
+                        // registers this step has just consumed
+                        tc_wait_ld();
+                        tc_reg_fence(a[(sb + 1) & 1][0]); tc_reg_fence(a[(sb + 1) & 1][1]);
+                        if (sb == kSB - 2) {   // every block of this tile has left TMEM: the buffer is free again
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(t_empty + 8 * (set * 2 + (tile & 1u)));
+                        }
+                        if (sb + 2 < kSB) {
+                            load_block(tile, sb + 2, a[sb & 1]);
+                        } else if (tl + 1 < tiles_item) {
+                            if (sb + 2 == kSB) open_tile(tile + 1);
+                            load_block(tile + 1, sb + 2 - kSB, a[sb & 1]);
+                        }
+                    }
+                }
+            // drain: the deepest chain position consumes the last block NLEV steps after it entered
+#pragma unroll 1
+            for (int dr = 0; dr < NLEV; ++dr) step(std::false_type{}, a[0], false);
         }
     }
     tc_fence_before();
@@ -468,17 +498,17 @@ bool tens_tc_supported(int kind, int d, int nlev, int order, int increments, int
 
 template <int NLEV, int KA>
 static int launch_tc_inst(const CUtensorMap& mx, const CUtensorMap& mz0, const CUtensorMap& mz1, const TcParams& p, cudaStream_t st) {
-    constexpr int S = KA == 1 ? 4 : 3;
+    constexpr int S = KA == 1 ? 3 : 2;   // stages of EACH set's B ring
     constexpr int NB = KA == 1 ? 16 : 8;
     auto kern = tens_seq_tc_kernel<NLEV, KA, S, NB>;
-    const size_t smem = 2 * (size_t)KA * kTcRows * 128 + (size_t)S * KA * kTcNT * 128 + 8 * (size_t)((NLEV + 1) * 32 + 66) * NB * 4 +
-                        16 * S + 80 + 16 + 1024;
+    const size_t smem = 2 * (size_t)KA * kTcRows * 128 + 2 * (size_t)S * KA * kTcNT * 128 + 8 * (size_t)((NLEV + 1) * 32 + 66) * NB * 4 +
+                        32 * S + 96 + 16 + 1024;
     if (smem > 232448) return GPSIG_E_UNSUPPORTED;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const long long nitems = (long long)p.ntiles * p.nch;
     const int grid = (int)(nitems < num_sms() ? nitems : num_sms());
-    kern<<<grid, 288, smem, st>>>(mx, mz0, mz1, p);
+    kern<<<grid, kTcThreads, smem, st>>>(mx, mz0, mz1, p);
     return check_launch();
 }
 

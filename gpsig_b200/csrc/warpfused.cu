@@ -40,10 +40,11 @@ constexpr int kWfAnchor = 3;  // strip-local anchor point (RBF mode 1)
 struct WfParams {
     const float* A;   // prepared row-side data    (rows i, rowsA, D)
     const float* B;   // prepared column-side data (rows j, rowsB, D)
-    const float* Bu;  // RBF anchored form of the column side: 2 (y_t - a(strip of t))      (rows j, rowsB, D)
-    const float* Bnu; //                                         -|y_t - a|^2               (rows j, rowsB)
-    const float* Banc;//                                         -a per strip               (rows j, nstrip, D)
-    int nstrip;
+    // RBF anchored form of the column side, padded to LP whole strips per sequence (points past the end are copies of the
+    // last one): row 8 s + 3 of Bu holds MINUS the anchor of strip s (its own u is zero and never read), the other rows
+    // u_t = 2 (y_t - a);  Bnu = -|y_t - a|^2
+    const float* Bu;   // (rows j, 8 LP, D)
+    const float* Bnu;  // (rows j, 8 LP)
     const unsigned* flag;  // RBF: float bits of max |u|^2 over the column side (NULL = never jumpy)
     int rowsA, rowsB;      // rowsA == steps per item (RBF: row 0 only primes the differencing)
     int LP, log2LP, G;
@@ -171,9 +172,12 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_warpfused_kernel(const W
     auto Pm = [&](int m) -> float& { return m < 2 * NPP ? ((m & 1) ? PP[m >> 1].y : PP[m >> 1].x) : PS; };
     auto Am = [&](int m, int j) -> float& { return m < 2 * NAP ? ((m & 1) ? AP[m >> 1][j].y : AP[m >> 1][j].x) : AS[j]; };
 
-    WfTrack tx, ty;      // item whose tiles are staged next (warp-uniform) / item this lane works on
+    WfTrack tx;          // item whose tiles are staged next (warp-uniform)
     wf_track_init(p, tx, wg);
-    ty = tx;
+    // where the results go, for the item staged last and the one before it (warp-uniform).  The last strip finishes an item
+    // LP - 2 steps into the NEXT period, after the next item has been staged: it always writes the "previous" one
+    int cur_j0 = 0, prev_j0 = 0;            // first column of the item's group
+    int cur_row = 0, prev_row = 0;          // output row
     int s = -l;          // row of this lane's current item (negative: not started)
     int par = 0;         // x-tile buffer of this lane's current item
     int par0 = 0;        // x-tile buffer the next staging fills (warp-uniform)
@@ -188,6 +192,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_warpfused_kernel(const W
         // ---- strip 0 enters a new item: the warp stages x_i (other buffer) and the y_j of the G pairs ----
         if (EV && stage) {
             const int i = tx.i, jg0 = wf_track_jg(p, tx) * p.G;
+            prev_j0 = cur_j0; prev_row = cur_row;
+            cur_j0 = jg0;
+            cur_row = p.diag ? 0 : (int)p.blk_out_row[tx.blk] + (i - p.blk_begin[tx.blk]);
             wf_track_next(p, tx);
             float4* dstx = reinterpret_cast<float4*>(xt + par0 * p.xfloats);
             const int perx = Lrow * C4;
@@ -206,18 +213,18 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_warpfused_kernel(const W
             }
             if (!p.diag || MODE == 1) {  // column side (diag, modes 0 / 2: the points are taken from the x tile)
                 float4* dsty = reinterpret_cast<float4*>(yt);
-                const int per = p.rowsB * C4;
+                const int yrows = MODE == 1 ? LP * W : p.rowsB;  // anchored form: whole strips
+                const int per = yrows * C4;
                 const float* ysrc = MODE == 1 ? p.Bu : p.B;
                 for (int g = 0; g < p.G; ++g) {
                     int jl = jg0 + g;
                     if (jl > p.n2 - 1) jl = p.n2 - 1;  // padding pair of a ragged last group
-                    const float4* srcy = reinterpret_cast<const float4*>(ysrc + (long long)jl * p.rowsB * D);
+                    const float4* srcy = reinterpret_cast<const float4*>(ysrc + (long long)jl * yrows * D);
                     for (int e = lane; e < per; e += 32) dsty[g * per + e] = __ldg(srcy + e);
-                    if (MODE == 1) {  // -|u|^2 of every strip point (points past the end are copies of the last one)
-                        float* dn = nut + par0 * p.nufloats + g * LP * W;
-                        for (int e = lane; e < LP * W; e += 32)  // the tail of a partial strip repeats the last point; strips
-                            dn[e] = e < p.nstrip * W                // entirely past the end are anchored AT the last point
-                                        ? __ldg(p.Bnu + (long long)jl * p.rowsB + (e < p.rowsB ? e : p.rowsB - 1)) : 0.f;
+                    if (MODE == 1) {  // -|u|^2 of every strip point
+                        float4* dn = reinterpret_cast<float4*>(nut + par0 * p.nufloats + g * LP * W);
+                        const float4* sn = reinterpret_cast<const float4*>(p.Bnu + (long long)jl * LP * W);
+                        for (int e = lane; e < LP * W / 4; e += 32) dn[e] = __ldg(sn + e);
                     }
                 }
             }
@@ -226,36 +233,26 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_warpfused_kernel(const W
         }
         // a strip that finished its item on the previous step moves on (always within the EV steps: strip l finishes at
         // period step l - 1, strip 0 on the last step of the period)
-        if (EV && s == Lrow) { s = 0; par ^= 1; wf_track_next(p, ty); }
+        if (EV && s == Lrow) { s = 0; par ^= 1; }
         const bool valid = CHECK ? (s >= 0 && T - l < total) : true;
         // ---- this strip enters the item: its column points move from the tile into registers ----
         if (EV && valid && s == 0) {
             if (MODE == 1) {
-                // everything was put into the anchored form once per call (wf_anchor_prep_kernel): plain copies
-                int jl = wf_track_jg(p, ty) * p.G + q;
-                if (jl > p.n2 - 1) jl = p.n2 - 1;
-                // a strip entirely past the end of the sequence stands for copies of the last point: anchored AT that point
-                // (u = 0 for every column, so that its anchor column evaluates the same value as the others)
-                const bool past = l >= p.nstrip;
-                const float4* sa = past ? reinterpret_cast<const float4*>(p.B + ((long long)jl * p.rowsB + p.rowsB - 1) * D)
-                                        : reinterpret_cast<const float4*>(p.Banc + ((long long)jl * p.nstrip + l) * D);
-                const float sgn = past ? -1.f : 1.f;  // Banc already holds -a
-#pragma unroll
-                for (int c = 0; c < C4; ++c) {
-                    const float4 v = __ldg(sa + c);
-                    nanc[2 * c] = make_float2(sgn * v.x, sgn * v.y);
-                    nanc[2 * c + 1] = make_float2(sgn * v.z, sgn * v.w);
-                }
+                // everything was put into the anchored form once per call (wf_anchor_prep_kernel), tails and strips past the
+                // end included: plain copies; the anchor's own row of the tile holds -a
+                const float4* src = reinterpret_cast<const float4*>(yt + ((size_t)q * LP * W + t0) * D);
 #pragma unroll
                 for (int u = 0; u < W; ++u) {
-                    const int t = t0 + u;
-                    const int tc = t < p.rowsB ? t : p.rowsB - 1;  // tail of a partial strip: copies of the last point
-                    const float4* src = reinterpret_cast<const float4*>(yt + ((size_t)q * p.rowsB + tc) * D);
 #pragma unroll
                     for (int c = 0; c < C4; ++c) {
-                        const float4 v = past ? make_float4(0.f, 0.f, 0.f, 0.f) : src[c];
-                        y[u][2 * c] = make_float2(v.x, v.y);
-                        y[u][2 * c + 1] = make_float2(v.z, v.w);
+                        const float4 v = src[u * C4 + c];
+                        if (u == kWfAnchor) {
+                            nanc[2 * c] = make_float2(v.x, v.y);
+                            nanc[2 * c + 1] = make_float2(v.z, v.w);
+                        } else {
+                            y[u][2 * c] = make_float2(v.x, v.y);
+                            y[u][2 * c + 1] = make_float2(v.z, v.w);
+                        }
                     }
                 }
             } else {
@@ -412,10 +409,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_warpfused_kernel(const W
             for (int i = 0; i < NPP; ++i) KP[i] = __fadd2_rn(KP[i], PP[i]);
             if (NLEV & 1) KS += PS;
             if (EV && s == Lrow - 1 && l == LP - 1) {
-                const int j = wf_track_jg(p, ty) * p.G + q;
+                const int j = prev_j0 + q;
                 if (j < p.n2) {
-                    float* o = p.diag ? p.out + j
-                                      : p.out + (p.blk_out_row[ty.blk] + (ty.i - p.blk_begin[ty.blk])) * p.ldo + j;
+                    float* o = p.out + (long long)prev_row * p.ldo + j;
                     o[0] = 1.f;
 #pragma unroll
                     for (int m = 0; m < NLEV; ++m) {
@@ -439,33 +435,36 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sigkern_warpfused_kernel(const W
         }
         for (long long T = base + LP; T < base + Lrow; ++T) step(no, no, T, false);
     }
+    prev_j0 = cur_j0; prev_row = cur_row;  // no staging any more: the item staged last is the one the tail finishes
     for (long long T = total; T < nsteps; ++T) step(yes, yes, T, false);  // the other strips finish the last item
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// column side of the anchored RBF form, once per call: for every point y_t (scaled as in prep mode 3) of every column
-// sequence, with a = the anchor of its strip (point 8 (t / 8) + 3, clamped to the last point):
-//     Bu = 2 (y_t - a),   Bnu = -|y_t - a|^2,   Banc[strip] = -a;   flag = max |y_t - a|^2 over the call (float bits)
+// column side of the anchored RBF form, once per call.  Every column sequence is padded to `rp` = 8 LP points (whole lane
+// strips; points past the end are copies of the last one).  For the point y_t (scaled as in prep mode 3), with a = the
+// anchor of its strip (point 8 (t / 8) + 3, clamped to the last point):
+//     Bu[t] = 2 (y_t - a)   -- except the row 8 (t / 8) + 3 itself, which holds -a (the kernel never reads the anchor's u),
+//     Bnu[t] = -|y_t - a|^2;   flag = max |y_t - a|^2 over the call (float bits)
+// A strip entirely past the end is anchored AT the last point (u = 0 everywhere), so its anchor column evaluates the same
+// value as its other columns.
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void wf_anchor_prep_kernel(const float* __restrict__ B, long long n, int rows, int D, int nstrip,
-                                      float* __restrict__ Bu, float* __restrict__ Bnu, float* __restrict__ Banc,
-                                      unsigned* __restrict__ flag) {
-    const long long total = n * rows;
+__global__ void wf_anchor_prep_kernel(const float* __restrict__ B, long long n, int rows, int D, int rp,
+                                      float* __restrict__ Bu, float* __restrict__ Bnu, unsigned* __restrict__ flag) {
+    const long long total = n * rp;
     float worst = 0.f;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const long long seq = idx / rows;
-        const int t = (int)(idx - seq * rows);
-        const int strip = t / kWfCols;
-        int ta = strip * kWfCols + kWfAnchor;
-        if (ta > rows - 1) ta = rows - 1;
-        const float* yp = B + idx * D;
+        const long long seq = idx / rp;
+        const int t = (int)(idx - seq * rp);
+        const int slot = t / kWfCols * kWfCols + kWfAnchor;
+        const int ta = slot < rows ? slot : rows - 1;
+        const int tc = t < rows ? t : rows - 1;
+        const float* yp = B + (seq * rows + tc) * D;
         const float* ap = B + (seq * rows + ta) * D;
         float acc = 0.f;
         for (int c = 0; c < D; ++c) {
             const float df = yp[c] - ap[c];
             acc = fmaf(df, df, acc);
-            Bu[idx * D + c] = df + df;
-            if (t == ta || (t == strip * kWfCols && ta < t)) Banc[(seq * nstrip + strip) * D + c] = -ap[c];
+            Bu[idx * D + c] = t == slot ? -ap[c] : df + df;
         }
         Bnu[idx] = -acc;
         worst = fmaxf(worst, acc);
@@ -474,29 +473,29 @@ __global__ void wf_anchor_prep_kernel(const float* __restrict__ B, long long n, 
     if ((threadIdx.x & 31) == 0 && worst > 0.f) atomicMax(flag, __float_as_uint(worst));  // non-negative floats order as uints
 }
 
+int wf_lanes_per_pair(int npts);
+
 size_t wf_anchor_bytes(long long n, int rows, int D) {
-    const int nstrip = (rows + kWfCols - 1) / kWfCols;
+    const int rp = wf_lanes_per_pair(rows) * kWfCols;
     auto up = [](size_t x) { return (x + 255) / 256 * 256; };
-    return up((size_t)n * rows * D * 4) + up((size_t)n * rows * 4) + up((size_t)n * nstrip * D * 4);
+    return up((size_t)n * rp * D * 4) + up((size_t)n * rp * 4);
 }
 
-// fills the three arrays (carved out of `buf`, wf_anchor_bytes() bytes) and the flag word
+// fills the two arrays (carved out of `buf`, wf_anchor_bytes() bytes) and the flag word
 int launch_wf_anchor_prep(const float* B, long long n, int rows, int D, void* buf, unsigned* flag, WfAnchored* out,
                           cudaStream_t st) {
-    const int nstrip = (rows + kWfCols - 1) / kWfCols;
+    const int rp = wf_lanes_per_pair(rows) * kWfCols;
     auto up = [](size_t x) { return (x + 255) / 256 * 256; };
     uint8_t* w = (uint8_t*)buf;
-    out->Bu = (float*)w; w += up((size_t)n * rows * D * 4);
-    out->Bnu = (float*)w; w += up((size_t)n * rows * 4);
-    out->Banc = (float*)w;
-    out->nstrip = nstrip;
+    out->Bu = (float*)w; w += up((size_t)n * rp * D * 4);
+    out->Bnu = (float*)w;
+    out->rows_padded = rp;
     cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(unsigned), st);
     if (e != cudaSuccess) return (int)e;
-    const long long total = n * rows;
+    const long long total = n * rp;
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)num_sms() * 8;
-    wf_anchor_prep_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(B, n, rows, D, nstrip, out->Bu, out->Bnu, out->Banc,
-                                                                               flag);
+    wf_anchor_prep_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(B, n, rows, D, rp, out->Bu, out->Bnu, flag);
     return check_launch();
 }
 
@@ -573,8 +572,7 @@ int launch_sigkern_warpfused(bool rbf, const float* A, const float* B, const WfA
     WfParams p;
     if (rbf && !anch) return fail(GPSIG_E_BADARG, "sigkern_warpfused: the RBF form needs the anchored column side");
     p.A = A; p.B = B; p.flag = flag; p.rowsA = rowsA; p.rowsB = rowsB;
-    p.Bu = rbf ? anch->Bu : nullptr; p.Bnu = rbf ? anch->Bnu : nullptr; p.Banc = rbf ? anch->Banc : nullptr;
-    p.nstrip = rbf ? anch->nstrip : 0;
+    p.Bu = rbf ? anch->Bu : nullptr; p.Bnu = rbf ? anch->Bnu : nullptr;
     p.LP = wf_lanes_per_pair(npts); p.log2LP = wf_log2(p.LP); p.G = 32 / p.LP;
     p.n2 = n2; p.upper_only = upper_only ? 1 : 0; p.diag = diag ? 1 : 0;
     p.NJG = (n2 + p.G - 1) / p.G;
@@ -598,7 +596,8 @@ int launch_sigkern_warpfused(bool rbf, const float* A, const float* B, const WfA
     int rc = GPSIG_E_UNSUPPORTED;
     if (rbf) {
         // anchored instantiation: y tile + -|u|^2 tile + anchor tile;  direct instantiation: plain y tile (diag: none)
-        p.yfloats = p.G * rowsB * D;
+        if (anch->rows_padded != p.LP * kWfCols) return fail(GPSIG_E_BADARG, "sigkern_warpfused: anchored form padded for another shape");
+        p.yfloats = p.G * p.LP * kWfCols * D;
         p.nufloats = p.G * p.LP * kWfCols;
         if (D == 4) rc = launch_wf_lev<1, 4>(nlev, p, st);
         if (D == 8) rc = launch_wf_lev<1, 8>(nlev, p, st);
