@@ -65,7 +65,6 @@ template <int NLEV, bool DIFF>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1)
 sigkern_fo_tma_kernel(const __grid_constant__ CUtensorMap tmap, const FoParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    constexpr int NA = NLEV > 1 ? NLEV - 1 : 1;
     const int nwarps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.nstages;
@@ -123,18 +122,29 @@ sigkern_fo_tma_kernel(const __grid_constant__ CUtensorMap tmap, const FoParams p
         for (long long n = 0; n < pre; n += 1 << p.log2R) issue();
     }
 
-    // ---- consumer state (per lane) ----
-    float A[NA][kW];
-    float psum[NLEV], ksum[NLEV];
-    float gp[kW + 1];
+    // ---- consumer state (per lane).  Issue slots bound this kernel (about 250 warp instructions per 2 KB row group), so
+    // the level state is kept as float2 pairs (A_{2i}, A_{2i+1}), (p_{2i}, p_{2i+1}) as in warpfused.cu: the NLEV - 1 adds
+    // A_m += p_m of a column become half as many add.f32x2, the second difference and the level sums likewise ----
+    constexpr int NAL = NLEV - 1;       // A_0 .. A_{NLEV-2}
+    constexpr int NAP = NAL / 2;        // pairs of A levels (+ one scalar level if NAL is odd)
+    constexpr int NPP = NLEV / 2;       // pairs of p levels (+ one scalar level if NLEV is odd)
+    float2 AP[NAP > 0 ? NAP : 1][kW];
+    float AS[kW];
+    float2 PP[NPP > 0 ? NPP : 1], KP[NPP > 0 ? NPP : 1];
+    float PS = 0.f, KS = 0.f;
+    float2 gdp[kW / 2];                 // DIFF: column differences g[t + 1] - g[t] of the previous row
 #pragma unroll
-    for (int m = 0; m < NLEV; ++m) { psum[m] = 0.f; ksum[m] = 0.f; }
+    for (int i = 0; i < (NPP > 0 ? NPP : 1); ++i) { PP[i] = make_float2(0.f, 0.f); KP[i] = make_float2(0.f, 0.f); }
 #pragma unroll
-    for (int m = 0; m < NA; ++m)
+    for (int j = 0; j < kW; ++j) {
+        AS[j] = 0.f;
 #pragma unroll
-        for (int j = 0; j < kW; ++j) A[m][j] = 0.f;
+        for (int i = 0; i < (NAP > 0 ? NAP : 1); ++i) AP[i][j] = make_float2(0.f, 0.f);
+    }
 #pragma unroll
-    for (int j = 0; j <= kW; ++j) gp[j] = 0.f;
+    for (int j = 0; j < kW / 2; ++j) gdp[j] = make_float2(0.f, 0.f);
+    auto Pm = [&](int m) -> float& { return m < 2 * NPP ? ((m & 1) ? PP[m >> 1].y : PP[m >> 1].x) : PS; };
+    auto Am = [&](int m, int j) -> float& { return m < 2 * NAP ? ((m & 1) ? AP[m >> 1][j].y : AP[m >> 1][j].x) : AS[j]; };
 
     long long n_l = -(long long)l;  // sequence number of the row this lane handles at the current step
     int rho = 0, stage = 0;
@@ -147,7 +157,7 @@ sigkern_fo_tma_kernel(const __grid_constant__ CUtensorMap tmap, const FoParams p
         float pin[NLEV];
 #pragma unroll
         for (int m = 0; m < NLEV; ++m) {
-            pin[m] = __shfl_up_sync(0xffffffffu, psum[m], 1);
+            pin[m] = __shfl_up_sync(0xffffffffu, Pm(m), 1);
             if (l == 0) pin[m] = 0.f;
         }
         const bool valid = (n_l >= 0) && (n_l < total);
@@ -169,12 +179,15 @@ sigkern_fo_tma_kernel(const __grid_constant__ CUtensorMap tmap, const FoParams p
                 if (l == LP - 1) g[kW] = g[kW - 1];
                 else asm volatile("ld.shared.f32 %0, [%1];" : "=f"(g[kW]) : "r"(base + off16));
                 first_row = (rho == 0);
-                if (!first_row) {
 #pragma unroll
-                    for (int j = 0; j < kW; ++j) d[j] = (g[j + 1] - g[j]) - (gp[j + 1] - gp[j]);
+                for (int j = 0; j < kW / 2; ++j) {
+                    const float2 gd = make_float2(g[2 * j + 1] - g[2 * j], g[2 * j + 2] - g[2 * j + 1]);
+                    if (!first_row) {
+                        const float2 dd = __ffma2_rn(gdp[j], make_float2(-1.f, -1.f), gd);   // signature_algs.py:26
+                        d[2 * j] = dd.x; d[2 * j + 1] = dd.y;
+                    }
+                    gdp[j] = gd;
                 }
-#pragma unroll
-                for (int j = 0; j <= kW; ++j) gp[j] = g[j];
             } else {
                 first_row = (rho == 0);
 #pragma unroll
@@ -193,30 +206,35 @@ sigkern_fo_tma_kernel(const __grid_constant__ CUtensorMap tmap, const FoParams p
         }
         if (valid && first_row) {
 #pragma unroll
-            for (int m = 0; m < NLEV; ++m) ksum[m] = 0.f;
+            for (int i = 0; i < (NPP > 0 ? NPP : 1); ++i) KP[i] = make_float2(0.f, 0.f);
+            KS = 0.f;
 #pragma unroll
-            for (int m = 0; m < NA; ++m)
+            for (int j = 0; j < kW; ++j) {
+                AS[j] = 0.f;
 #pragma unroll
-                for (int j = 0; j < kW; ++j) A[m][j] = 0.f;
+                for (int i = 0; i < (NAP > 0 ? NAP : 1); ++i) AP[i][j] = make_float2(0.f, 0.f);
+            }
         }
         // ---- the recursion: 2 FP ops per entry per level ----
 #pragma unroll
-        for (int m = 0; m < NLEV; ++m) psum[m] = pin[m];
+        for (int m = 0; m < NLEV; ++m) Pm(m) = pin[m];
 #pragma unroll
         for (int j = 0; j < kW; ++j) {
             const float dj = d[j];
+            float pn[NLEV];  // p_m after this column (levels >= 1 read the OLD A_{m-1} and the OLD p_m)
 #pragma unroll
-            for (int m = NLEV - 1; m >= 1; --m) {
-                const float a_prev = A[m - 1][j];
-                if (m < NLEV - 1) A[m][j] += psum[m];
-                psum[m] = fmaf(dj, a_prev, psum[m]);
-            }
-            if (NLEV > 1) A[0][j] += psum[0];
-            psum[0] += dj;
+            for (int m = 1; m < NLEV; ++m) pn[m] = fmaf(dj, Am(m - 1, j), Pm(m));
+            pn[0] = Pm(0) + dj;
+#pragma unroll
+            for (int i = 0; i < NAP; ++i) AP[i][j] = __fadd2_rn(AP[i][j], PP[i]);
+            if (NAL & 1) AS[j] += Pm(NAL - 1);
+#pragma unroll
+            for (int m = 0; m < NLEV; ++m) Pm(m) = pn[m];
         }
         if (valid) {
 #pragma unroll
-            for (int m = 0; m < NLEV; ++m) ksum[m] += psum[m];
+            for (int i = 0; i < NPP; ++i) KP[i] = __fadd2_rn(KP[i], PP[i]);
+            if (NLEV & 1) KS += PS;
             if (rho == Lin - 1 && l == LP - 1) {
                 int i, jg;
                 decode_item(p, item, i, jg);
@@ -225,7 +243,8 @@ sigkern_fo_tma_kernel(const __grid_constant__ CUtensorMap tmap, const FoParams p
                     float* o = p.out + (long long)(p.i_off + i) * p.ldo + p.j_off + j;
                     o[0] = 1.f;
 #pragma unroll
-                    for (int m = 0; m < NLEV; ++m) o[(long long)(m + 1) * p.out_level_stride] = ksum[m];
+                    for (int m = 0; m < NLEV; ++m)
+                        o[(long long)(m + 1) * p.out_level_stride] = m < 2 * NPP ? ((m & 1) ? KP[m >> 1].y : KP[m >> 1].x) : KS;
                 }
             }
             if (++rho == Lin) { rho = 0; item += NW; }

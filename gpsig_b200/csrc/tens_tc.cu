@@ -48,7 +48,7 @@ struct TcParams {
     const unsigned* flag;    // float bits of max |x - c|^2 (scaled)
     int ntiles, nch, chunk;  // row tiles, sequence chunks, sequences per chunk
     long long nz, n;
-    int Lp;                  // padded sequence length (multiple of 64)
+    int L, Lp;               // sequence length, padded sequence length (multiple of 64)
     float* out;              // (NLEV + 1, nz, n)
 };
 
@@ -270,7 +270,11 @@ tens_seq_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
             const int lag = pad ? 1 : row.p + 1;                   // this lane works on block (step - lag)
             const int src = (pad || row.p == 0) ? 32 : lane - 1;    // whose prefix it multiplies by (32 = the ones row)
             const int src_swz = src == 32 ? 0 : ((src >> 1) & (C4 - 1));
-            const int per_seq = tiles_per_seq * kSB;
+            // blocks of the last tile that hold real time steps (rounded up to a pair: the register buffer of a block is its
+            // parity); the padding behind them repeats the last point -- zero increments -- and is skipped
+            int last_nb = (((p.L - (tiles_per_seq - 1) * kTcNT + NB - 1) / NB) + 1) & ~1;
+            if (last_nb > kSB) last_nb = kSB;
+            const int per_seq = (tiles_per_seq - 1) * kSB + last_nb;
             const int tiles_item = nseq_set * tiles_per_seq;
             float a[2][2][NB];         // [register buffer][z^0 / z^1 accumulator][time step]
             float vprev = 0.f, carry = 0.f;
@@ -346,28 +350,37 @@ tens_seq_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
             tc_wait_ld();
             tc_reg_fence(a[0][0]); tc_reg_fence(a[0][1]); tc_reg_fence(a[1][0]); tc_reg_fence(a[1][1]);
             int tl = 0;   // tile of the item
-            for (int s = 0; s < nseq_set; ++s)
-                for (int tt = 0; tt < tiles_per_seq; ++tt, ++tile, ++tl) {
+            // FULL: every tile uses all its blocks (the sequence length is within a pair of blocks of a multiple of 64) --
+            // the loop over blocks has compile-time bounds; otherwise the last tile of a sequence stops early
+            auto run_tiles = [&](auto full_c) {
+                constexpr bool FULL = decltype(full_c)::value;
+                for (int s = 0; s < nseq_set; ++s)
+                    for (int tt = 0; tt < tiles_per_seq; ++tt, ++tile, ++tl) {
+                        const int nb = FULL ? kSB : (tt == tiles_per_seq - 1 ? last_nb : kSB);   // blocks of this tile (even)
 #pragma unroll
-                    for (int sb = 0; sb < kSB; ++sb) {
-                        step(std::true_type{}, a[sb & 1], tt == 0 && sb == 0);
-                        // block (sb + 1) -- loaded a step ago -- is complete after this wait; block (sb + 2) takes the
-                        // registers this step has just consumed
-                        tc_wait_ld();
-                        tc_reg_fence(a[(sb + 1) & 1][0]); tc_reg_fence(a[(sb + 1) & 1][1]);
-                        if (sb == kSB - 2) {   // every block of this tile has left TMEM: the buffer is free again
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(t_empty + 8 * (set * 2 + (tile & 1u)));
-                        }
-                        if (sb + 2 < kSB) {
-                            load_block(tile, sb + 2, a[sb & 1]);
-                        } else if (tl + 1 < tiles_item) {
-                            if (sb + 2 == kSB) open_tile(tile + 1);
-                            load_block(tile + 1, sb + 2 - kSB, a[sb & 1]);
+                        for (int sb = 0; sb < kSB; ++sb) {
+                            if (!FULL && sb >= nb) break;
+                            step(std::true_type{}, a[sb & 1], tt == 0 && sb == 0);
+                            // block (sb + 1) -- loaded a step ago -- is complete after this wait; block (sb + 2) takes the
+                            // registers this step has just consumed
+                            tc_wait_ld();
+                            tc_reg_fence(a[(sb + 1) & 1][0]); tc_reg_fence(a[(sb + 1) & 1][1]);
+                            if (sb == nb - 2) {    // every block of this tile that is used has left TMEM: the buffer is free
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(t_empty + 8 * (set * 2 + (tile & 1u)));
+                            }
+                            if (sb + 2 < nb) {
+                                load_block(tile, sb + 2, a[sb & 1]);
+                            } else if (tl + 1 < tiles_item) {   // sb = nb - 2 (even) / nb - 1 (odd): blocks 0 / 1 of the next tile
+                                if ((sb & 1) == 0) open_tile(tile + 1);
+                                load_block(tile + 1, sb & 1, a[sb & 1]);
+                            }
                         }
                     }
-                }
+            };
+            if (last_nb == kSB) run_tiles(std::true_type{});
+            else run_tiles(std::false_type{});
             // drain: the deepest chain position consumes the last block NLEV steps after it entered
 #pragma unroll 1
             for (int dr = 0; dr < NLEV; ++dr) step(std::false_type{}, a[0], false);
@@ -585,7 +598,7 @@ int launch_tens_seq_tc(const float* Z, long long nz, const float* X, long long n
         if ((rc = encode_tensor_map_f32(&mz1, Z1, 2, dz, strides, bz, 1))) return done(rc);
     }
     TcParams p;
-    p.rows = drows; p.flag = flag; p.ntiles = ntiles; p.nz = nz; p.n = n; p.Lp = Lp; p.out = out;
+    p.rows = drows; p.flag = flag; p.ntiles = ntiles; p.nz = nz; p.n = n; p.L = L; p.Lp = Lp; p.out = out;
     // chunks of sequences: enough items to balance 148 SMs (a few per SM), an even number of sequences per chunk
     long long chunk = 64;
     while (chunk > 8 && (long long)ntiles * ((n + chunk - 1) / chunk) < 4LL * num_sms()) chunk >>= 1;

@@ -64,15 +64,17 @@ def _check(feat, kern):
         raise NotImplementedError("feat must be InducingTensors or InducingSequences")
 
 
-def Kuu_Kuf_Kff(feat, kern, X_new, *, jitter=0.0, full_f_cov=False):
+def Kuu_Kuf_Kff(feat, kern, X_new, *, jitter=0.0, full_f_cov=False, literal=False):
     """inducing_variables.py:51-66 (tensors) / :122-137 (sequences).  full_f_cov=True raises NameError in the reference
-    (tf.shape(X) with X undefined, quirk Q5); the evident intent (jitter * I on Kxx) is implemented."""
+    (tf.shape(X) with X undefined, quirk Q5); the evident intent (jitter * I on Kxx) is implemented.  literal=True
+    (sequences only) reproduces the reference's double normalisation of Kzx (kernels.py:713 then :750, quirk Q4) -- what
+    the golden vectors of the unmodified reference hold; the default divides once."""
     _check(feat, kern)
     seq = isinstance(feat, InducingSequences)
     lv = bool(feat.learn_weights)
     if seq:
         Z = feat.Z.reshape(len(feat), -1)
-        Kzz, Kzx, Kxx = kern.K_seq_n_seq_covs(Z, X_new, full_X2_cov=full_f_cov, return_levels=lv)
+        Kzz, Kzx, Kxx = kern.K_seq_n_seq_covs(Z, X_new, full_X2_cov=full_f_cov, return_levels=lv, literal=literal)
     else:
         Kzz, Kzx, Kxx = kern.K_tens_n_seq_covs(feat.Z, X_new, full_X_cov=full_f_cov, return_levels=lv,
                                                increments=feat.increments)
