@@ -50,6 +50,7 @@ struct TcParams {
     long long nz, n;
     int L, Lp;               // sequence length, padded sequence length (multiple of 64)
     float* out;              // (NLEV + 1, nz, n)
+    const float* zscale;     // ZOUT layout: 2^(-|z|^2) per A row, z^0 rows then z^1 rows (2 x ntiles x 128)
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------------------
@@ -112,7 +113,8 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr) {
 constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcNT >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
 
 // ---- the kernel ----------------------------------------------------------------------------------------------------
-// KA = 128-byte K atoms per operand row (1: K = 32 slots, d <= 8;  2: K = 64, d <= 19);  S = stages of the B ring;
+// KA = 128-byte K atoms per operand row (1: K = 32 slots, d <= 8, and d = 9, 10 in the ZOUT layout;  2: K = 64, d <= 19);
+// S = stages of each B ring;
 // NB = time steps per epilogue block (16, or 8 where shared memory is short)
 // register fence: the values of a completed tcgen05.ld may only be read after tcgen05.wait::ld; the empty volatile asm
 // keeps its place after the (volatile) wait and every use of v depends on it
@@ -124,7 +126,7 @@ __device__ __forceinline__ void tc_reg_fence(float (&v)[N]) {
                           "+f"(v[i + 7]));
 }
 
-template <int NLEV, int KA, int S, int NB>
+template <int NLEV, int KA, int S, int NB, bool ZOUT>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tens_seq_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapZ0,
                    const __grid_constant__ CUtensorMap mapZ1, const TcParams p) {
@@ -265,6 +267,13 @@ tens_seq_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
             const int nseq_set = n0 + set < n1 ? (n1 - n0 - set + 1) / 2 : 0;
             if (nseq_set == 0) continue;
             const TcRow row = p.rows[(long long)zt * kTcRows + quarter * 32 + lane];
+            // ZOUT: the z-side norm is not in the MMA (no room for its slots): kappa = 2^D * 2^(-|z|^2); padding rows carry 0
+            float zs0 = 1.f, zs1 = 1.f;
+            if (ZOUT) {
+                const long long ri = (long long)zt * kTcRows + quarter * 32 + lane;
+                zs0 = p.zscale[ri];
+                zs1 = p.zscale[(long long)p.ntiles * kTcRows + ri];
+            }
             const bool pad = row.m == 0;
             const bool last = !pad && row.p == row.m - 1;
             const int lag = pad ? 1 : row.p + 1;                   // this lane works on block (step - lag)
@@ -312,7 +321,8 @@ tens_seq_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
                     float hnew[NB];
 #pragma unroll
                     for (int t = 0; t < NB; ++t) {
-                        const float v = tc_ex2(blk[1][t]) - tc_ex2(blk[0][t]);   // kernels.py:330
+                        const float v = ZOUT ? fmaf(tc_ex2(blk[1][t]), zs1, -(tc_ex2(blk[0][t]) * zs0))   // kernels.py:330
+                                             : tc_ex2(blk[1][t]) - tc_ex2(blk[0][t]);
                         if (t == 0) vprev = first_block ? v : vprev;            // first time step of a sequence: no increment yet
                         hnew[t] = v - vprev;                                    // signature_algs.py:114
                         vprev = v;
@@ -428,7 +438,7 @@ __global__ void __launch_bounds__(256) tc_centre_kernel(const float* __restrict_
 
 // B operand: one row per (sequence, padded time step); rows past the end of a sequence repeat its last point
 __global__ void tc_prep_x_kernel(const float* __restrict__ X, long long n, int L, int Lp, int d, const float* __restrict__ inv_ls,
-                                 const float* __restrict__ sums, float inv_rows, int KW, float* __restrict__ out,
+                                 const float* __restrict__ sums, float inv_rows, int KW, int zout, float* __restrict__ out,
                                  unsigned* __restrict__ flag) {
     const float rs = 0.8493218002880191f;  // sqrt(log2(e) / 2): log2 k = -|x' - z'|^2
     float worst = 0.f;
@@ -448,9 +458,14 @@ __global__ void tc_prep_x_kernel(const float* __restrict__ X, long long n, int L
         }
         float p1, p2, p3;
         tf32_split3(-nn, p1, p2, p3);
-        o[3 * d] = p1; o[3 * d + 1] = p2; o[3 * d + 2] = p3;
-        o[3 * d + 3] = 1.f; o[3 * d + 4] = 1.f; o[3 * d + 5] = 1.f;
-        for (int c = 3 * d + 6; c < KW; ++c) o[c] = 0.f;
+        if (zout) {  // 3 d + 2 slots: -|x|^2 in two pieces (2^-22 |x|^2 left over), the z norm is applied in the epilogue
+            o[3 * d] = p1; o[3 * d + 1] = p2;
+            for (int c = 3 * d + 2; c < KW; ++c) o[c] = 0.f;
+        } else {
+            o[3 * d] = p1; o[3 * d + 1] = p2; o[3 * d + 2] = p3;
+            o[3 * d + 3] = 1.f; o[3 * d + 4] = 1.f; o[3 * d + 5] = 1.f;
+            for (int c = 3 * d + 6; c < KW; ++c) o[c] = 0.f;
+        }
         worst = fmaxf(worst, nn);
     }
     for (int o2 = 16; o2 > 0; o2 >>= 1) worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, o2));
@@ -460,7 +475,7 @@ __global__ void tc_prep_x_kernel(const float* __restrict__ X, long long n, int L
 // A operands: row r of the row map -> the z^0 (w = 0) and z^1 (w = 1) points of its (tensor, component); padding rows are zero
 __global__ void tc_prep_z_kernel(const float* __restrict__ Z, long long nz, int d, const float* __restrict__ inv_ls,
                                  const float* __restrict__ sums, float inv_rows, const TcRow* __restrict__ rows, long long nrows,
-                                 int KW, float* __restrict__ out0, float* __restrict__ out1) {
+                                 int KW, float* __restrict__ zscale, float* __restrict__ out0, float* __restrict__ out1) {
     const float rs = 0.8493218002880191f;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < 2 * nrows; idx += (long long)gridDim.x * blockDim.x) {
         const long long r = idx >> 1;
@@ -469,6 +484,7 @@ __global__ void tc_prep_z_kernel(const float* __restrict__ Z, long long nz, int 
         const TcRow row = rows[r];
         if (row.m == 0) {
             for (int c = 0; c < KW; ++c) o[c] = 0.f;
+            if (zscale) zscale[(long long)w * nrows + r] = 0.f;
             continue;
         }
         const float* z0 = Z + (((long long)row.k * nz + row.z) * 2 + w) * d;
@@ -481,11 +497,17 @@ __global__ void tc_prep_z_kernel(const float* __restrict__ Z, long long nz, int 
             const float hi = tf32_rn(v2), lo = tf32_rn(v2 - hi);
             o[c] = hi; o[d + c] = hi; o[2 * d + c] = lo;
         }
-        float p1, p2, p3;
-        tf32_split3(-nn, p1, p2, p3);
-        o[3 * d] = 1.f; o[3 * d + 1] = 1.f; o[3 * d + 2] = 1.f;
-        o[3 * d + 3] = p1; o[3 * d + 4] = p2; o[3 * d + 5] = p3;
-        for (int c = 3 * d + 6; c < KW; ++c) o[c] = 0.f;
+        if (zscale) {
+            o[3 * d] = 1.f; o[3 * d + 1] = 1.f;
+            for (int c = 3 * d + 2; c < KW; ++c) o[c] = 0.f;
+            zscale[(long long)w * nrows + r] = exp2f(-nn);
+        } else {
+            float p1, p2, p3;
+            tf32_split3(-nn, p1, p2, p3);
+            o[3 * d] = 1.f; o[3 * d + 1] = 1.f; o[3 * d + 2] = 1.f;
+            o[3 * d + 3] = p1; o[3 * d + 4] = p2; o[3 * d + 5] = p3;
+            for (int c = 3 * d + 6; c < KW; ++c) o[c] = 0.f;
+        }
     }
 }
 
@@ -509,11 +531,11 @@ bool tens_tc_supported(int kind, int d, int nlev, int order, int increments, int
            env_knobs().tens_tc != 0;
 }
 
-template <int NLEV, int KA>
+template <int NLEV, int KA, bool ZOUT>
 static int launch_tc_inst(const CUtensorMap& mx, const CUtensorMap& mz0, const CUtensorMap& mz1, const TcParams& p, cudaStream_t st) {
     constexpr int S = KA == 1 ? 3 : 2;   // stages of EACH set's B ring
     constexpr int NB = KA == 1 ? 16 : 8;
-    auto kern = tens_seq_tc_kernel<NLEV, KA, S, NB>;
+    auto kern = tens_seq_tc_kernel<NLEV, KA, S, NB, ZOUT>;
     const size_t smem = 2 * (size_t)KA * kTcRows * 128 + 2 * (size_t)S * KA * kTcNT * 128 + 8 * (size_t)((NLEV + 1) * 32 + 66) * NB * 4 +
                         32 * S + 96 + 16 + 1024;
     if (smem > 232448) return GPSIG_E_UNSUPPORTED;
@@ -525,16 +547,16 @@ static int launch_tc_inst(const CUtensorMap& mx, const CUtensorMap& mz0, const C
     return check_launch();
 }
 
-template <int KA>
+template <int KA, bool ZOUT>
 static int launch_tc_lev(int nlev, const CUtensorMap& mx, const CUtensorMap& mz0, const CUtensorMap& mz1, const TcParams& p,
                          cudaStream_t st) {
     switch (nlev) {
-        case 1: return launch_tc_inst<1, KA>(mx, mz0, mz1, p, st);
-        case 2: return launch_tc_inst<2, KA>(mx, mz0, mz1, p, st);
-        case 3: return launch_tc_inst<3, KA>(mx, mz0, mz1, p, st);
-        case 4: return launch_tc_inst<4, KA>(mx, mz0, mz1, p, st);
-        case 5: return launch_tc_inst<5, KA>(mx, mz0, mz1, p, st);
-        case 6: return launch_tc_inst<6, KA>(mx, mz0, mz1, p, st);
+        case 1: return launch_tc_inst<1, KA, ZOUT>(mx, mz0, mz1, p, st);
+        case 2: return launch_tc_inst<2, KA, ZOUT>(mx, mz0, mz1, p, st);
+        case 3: return launch_tc_inst<3, KA, ZOUT>(mx, mz0, mz1, p, st);
+        case 4: return launch_tc_inst<4, KA, ZOUT>(mx, mz0, mz1, p, st);
+        case 5: return launch_tc_inst<5, KA, ZOUT>(mx, mz0, mz1, p, st);
+        case 6: return launch_tc_inst<6, KA, ZOUT>(mx, mz0, mz1, p, st);
     }
     return GPSIG_E_UNSUPPORTED;
 }
@@ -542,25 +564,30 @@ static int launch_tc_lev(int nlev, const CUtensorMap& mx, const CUtensorMap& mz0
 // Z (T, nz, 2, d), X (n, L, d) RAW; inv_ls may be NULL; out (nlev + 1, nz, n); flag: one device word (written here)
 int launch_tens_seq_tc(const float* Z, long long nz, const float* X, long long n, int L, int d, const float* inv_ls, int nlev,
                        float* out, unsigned* flag, cudaStream_t st) {
-    const int KA = 3 * d + 6 <= 32 ? 1 : 2, KW = 32 * KA;
+    // operand layouts: d <= 8: 3 d + 6 slots in one 32-slot atom;  d = 9, 10: 3 d + 2 slots in one atom with the z norm applied
+    // in the epilogue (ZOUT);  d <= 19: two atoms
+    const bool zout = 3 * d + 6 > 32 && 3 * d + 2 <= 32;
+    const int KA = (3 * d + 6 <= 32 || zout) ? 1 : 2, KW = 32 * KA;
     const int Lp = (L + kTcNT - 1) / kTcNT * kTcNT;
     std::vector<TcRow> rows;
     tc_row_map(nz, nlev, rows);
     const long long nrows = (long long)rows.size();
     const int ntiles = (int)(nrows / kTcRows);
-    // scratch: sums (d floats, zeroed) | row map | Xop | Z0op | Z1op
+    // scratch: sums (d floats, zeroed) | row map | Xop | Z0op | Z1op | z scales (ZOUT)
     auto up = [](size_t x) { return (x + 1023) / 1024 * 1024; };
     const size_t b_sums = up(64 * 4), b_rows = up((size_t)nrows * sizeof(TcRow)), b_x = up((size_t)n * Lp * KW * 4),
                  b_z = up((size_t)nrows * KW * 4);
     uint8_t* buf = nullptr;
-    cudaError_t e = cudaMallocAsync((void**)&buf, b_sums + b_rows + b_x + 2 * b_z + 1024, st);
+    const size_t b_zs = up((size_t)2 * nrows * 4);
+    cudaError_t e = cudaMallocAsync((void**)&buf, b_sums + b_rows + b_x + 2 * b_z + b_zs + 1024, st);
     if (e != cudaSuccess) return (int)e;
     uint8_t* w = (uint8_t*)(((uintptr_t)buf + 1023) / 1024 * 1024);
     float* sums = (float*)w; w += b_sums;
     TcRow* drows = (TcRow*)w; w += b_rows;
     float* Xop = (float*)w; w += b_x;
     float* Z0 = (float*)w; w += b_z;
-    float* Z1 = (float*)w;
+    float* Z1 = (float*)w; w += b_z;
+    float* zscale = zout ? (float*)w : nullptr;
     int rc = GPSIG_OK;
     auto done = [&](int code) { cudaFreeAsync(buf, st); return code; };
     if ((e = cudaMemsetAsync(sums, 0, b_sums, st)) != cudaSuccess) return done((int)e);
@@ -579,12 +606,12 @@ int launch_tens_seq_tc(const float* Z, long long nz, const float* X, long long n
         tc_centre_kernel<<<1, 256, 0, st>>>(Z, zpts, d, inv_ls, sums);
         if ((rc = check_launch())) return done(rc);
         long long blocks = (n * Lp + 255) / 256;
-        tc_prep_x_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(X, n, L, Lp, d, inv_ls, sums, 1.f / (float)zpts, KW, Xop,
+        tc_prep_x_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(X, n, L, Lp, d, inv_ls, sums, 1.f / (float)zpts, KW, zout ? 1 : 0, Xop,
                                                                              flag);
         if ((rc = check_launch())) return done(rc);
         blocks = (2 * nrows + 255) / 256;
         tc_prep_z_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(Z, nz, d, inv_ls, sums, 1.f / (float)zpts, drows, nrows,
-                                                                             KW, Z0, Z1);
+                                                                             KW, zscale, Z0, Z1);
         if ((rc = check_launch())) return done(rc);
     }
     CUtensorMap mx, mz0, mz1;
@@ -598,7 +625,7 @@ int launch_tens_seq_tc(const float* Z, long long nz, const float* X, long long n
         if ((rc = encode_tensor_map_f32(&mz1, Z1, 2, dz, strides, bz, 1))) return done(rc);
     }
     TcParams p;
-    p.rows = drows; p.flag = flag; p.ntiles = ntiles; p.nz = nz; p.n = n; p.L = L; p.Lp = Lp; p.out = out;
+    p.rows = drows; p.flag = flag; p.ntiles = ntiles; p.nz = nz; p.n = n; p.L = L; p.Lp = Lp; p.out = out; p.zscale = zscale;
     // chunks of sequences: enough items to balance 148 SMs (a few per SM), an even number of sequences per chunk
     long long chunk = 64;
     while (chunk > 8 && (long long)ntiles * ((n + chunk - 1) / chunk) < 4LL * num_sms()) chunk >>= 1;
@@ -606,7 +633,8 @@ int launch_tens_seq_tc(const float* Z, long long nz, const float* X, long long n
     p.nch = (int)((n + chunk - 1) / chunk);
     {
         ProfScope prof(GPSIG_PROF_TENS, st, (double)nz * n);
-        rc = KA == 1 ? launch_tc_lev<1>(nlev, mx, mz0, mz1, p, st) : launch_tc_lev<2>(nlev, mx, mz0, mz1, p, st);
+        rc = zout ? launch_tc_lev<1, true>(nlev, mx, mz0, mz1, p, st)
+                  : (KA == 1 ? launch_tc_lev<1, false>(nlev, mx, mz0, mz1, p, st) : launch_tc_lev<2, false>(nlev, mx, mz0, mz1, p, st));
     }
     return done(rc);
 }

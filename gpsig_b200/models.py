@@ -218,7 +218,7 @@ class SVGP:
             return a.to(device=dev, dtype=dtype)
         return torch.as_tensor(np.asarray(a)).to(device=dev, dtype=dtype)
 
-    def _build_predict(self, X_new, full_cov=False, full_output_cov=False, return_Kzz=False):
+    def _build_predict(self, X_new, full_cov=False, full_output_cov=False, return_Kzz=False, return_q=False):
         """models.py:61-73.  The covariances arrive in fp32 from the device path; the conditional runs in float64."""
         Kzz, Kzx, Kxx = Kuu_Kuf_Kff(self.feature, self.kern, X_new, jitter=settings.jitter, full_f_cov=full_cov)
         dev = Kzz.device
@@ -230,6 +230,8 @@ class SVGP:
         f_mean, f_var = base_conditional(Kzx, Kzz, Kxx, q_mu, full_cov=full_cov, q_sqrt=q_sqrt, white=self.whiten)
         if not isinstance(self.mean_function, Zero):                                               # models.py:67
             f_mean = f_mean + self.mean_function(self._dev(X_new, dev).reshape(X_new.shape[0], -1))
+        if return_q:   # the bound needs q_mu / q_sqrt on the device again (KL): uploaded once per step, not twice
+            return f_mean, f_var, (Kzz if return_Kzz else None), q_mu, q_sqrt
         if return_Kzz:
             return f_mean, f_var, Kzz
         return f_mean, f_var
@@ -294,14 +296,9 @@ class SVGP:
         if X is None:
             X, Y = self._batch()
         num_samples = X.shape[0]
-        if self.whiten:
-            f_mean, f_var = self._build_predict(X)
-            Kzz = None
-        else:
-            f_mean, f_var, Kzz = self._build_predict(X, return_Kzz=True)
+        f_mean, f_var, Kzz, q_mu, q_sqrt = self._build_predict(X, return_Kzz=not self.whiten, return_q=True)
         dev = f_mean.device
-        q_sqrt = self._dev(self.q_sqrt, dev)
-        KL = gauss_kl(self._dev(self.q_mu, dev), torch.tril(q_sqrt) if q_sqrt.dim() == 3 else q_sqrt, K=Kzz)
+        KL = gauss_kl(q_mu, q_sqrt, K=Kzz)                     # q_sqrt is already lower-triangular (_build_predict)
         var_exp = self.likelihood.variational_expectations(f_mean, f_var, self._dev(Y, dev))
         scale = float(self.num_data) / float(num_samples)
         return torch.sum(var_exp) * scale - KL
