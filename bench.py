@@ -469,8 +469,15 @@ def run_ours(args, wl):
     prof = read_profile(lib, _lib, PROF_CLASSES)
     lib.gpsig_profile_reset()
     launches = torch.tensor([l1 - l0], device=dev, dtype=torch.int64)
+    per_rank = None
     if world > 1:
         dist.all_reduce(launches)
+        # the dominant kernel's time on EVERY rank (the step time is the max over ranks: a slow GPU or an unbalanced shard
+        # shows here, a slow collective does not)
+        mine = torch.tensor([(prof["fused"][0] + prof["tens"][0]) / args.steps], device=dev, dtype=torch.float64)
+        allk = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allk, mine)
+        per_rank = [round(float(t.item()), 3) for t in allk]
 
     # e2e: host buffers in, host buffer out
     step_e2e()
@@ -642,6 +649,7 @@ def run_ours(args, wl):
                 "host_result": ("one pinned host buffer shared by the ranks; every rank writes its slab" if world > 1
                                 else "pinned host buffer")},
         "gpu_launches": int(launches.item()),
+        "per_rank_kernel_ms": per_rank,
         "clocks": clocks,
         "roofline": roofline,
         "pipeline": pipeline,

@@ -13,16 +13,21 @@
 // the centre the coordinates are taken from (the mean of the tensor points): the prep kernel leaves max |x - c|^2 in a flag word, this
 // kernel returns at once when it exceeds kTcRadius2, and the CUDA-core kernel of tens.cu (anchored differences, good
 // anywhere) returns at once when it does not -- both are launched, no host synchronisation.
+// d = 9, 10 (3d + 6 = 33, 36 slots: one too many atoms) use the ZOUT layout instead: nx in TWO pieces and the z norm out
+// of the MMA, applied as a per-row factor in the epilogue (v = 2^D1 * 2^-|z1|^2 - 2^D0 * 2^-|z0|^2): 3d + 2 <= 32 slots.
 //
 // One CTA per SM, persistent over work items (tile of 128 rows x chunk of sequences):
 //   * rows: the (tensor, component) pairs.  A level's components form a CHAIN (r_p[t] = h_p[t] * sum_{t'<t} r_{p-1}[t']);
 //     chains are packed into warps of 32 TMEM lanes without ever splitting one (row map built on the host), lane = row.
-//   * warp 8, one elected lane: TMA loads (A tiles once per item, B tiles of 64 time steps through a ring) and the MMAs --
-//     per tile 2 x (K/8) tcgen05.mma (M=128, N=64): D0 = exponents against the z^0 points, D1 against the z^1 points,
-//     side by side in TMEM (128 columns per buffer, 2 buffers for each of the 2 warp sets = all 512 columns).
+//   * warps 8 and 9, one elected lane each: the producers, ONE PER WARP SET (a single producer serving both sets in program
+//     order made them run in lockstep).  TMA loads (A tiles once per item by producer 0, B tiles of 64 time steps through
+//     the set's own ring) and the MMAs -- per tile 2 x (K/8) tcgen05.mma (M=128, N=64): D0 = exponents against the z^0
+//     points, D1 against the z^1 points, side by side in TMEM (128 columns per buffer, 2 buffers for each of the 2 warp
+//     sets = all 512 columns).
 //   * warps 0-7: two sets of 4 (one warp per TMEM lane quarter); set s takes the sequences n = s (mod 2) of the chunk.  The
-//     blocks of NB time steps of a set's sequences form one stream.  At step b every thread reads its row's 2 x NB
-//     exponents of block b (tcgen05.ld 32x32b), v = 2^D1 - 2^D0, h = time increment of v, and parks h in a per-warp
+//     blocks of NB time steps of a set's sequences form one stream.  At step b every thread has its row's 2 x NB
+//     exponents of block b in registers (tcgen05.ld 32x32b, double buffered: block b + 2 is requested when block b has
+//     been consumed), v = 2^D1 - 2^D0, h = time increment of v, and parks h in a per-warp
 //     shared-memory FIFO.  The chain runs SKEWED: the lane at chain position p works on block b - 1 - p (its h from the
 //     FIFO, the exclusive prefix c_in of its predecessor from a double-buffered patch the predecessor filled one step
 //     earlier): r = h * c_in, running prefix, hand the prefix on.  One round per block instead of one per level, and the
