@@ -18,10 +18,33 @@ from . import settings
 from .inducing_variables import InducingTensors, InducingSequences, Kuu_Kuf_Kff
 
 
+_pending_info = []
+
+
+def _cholesky(K):
+    """torch.linalg.cholesky raises on failure, which costs a device synchronisation in the middle of a step (the host
+    cannot queue the rest of the step behind the Kuf kernel).  On the device the status word is kept instead and checked
+    where the step synchronises anyway (check_cholesky: compute_log_likelihood, optimize, predict_f)."""
+    if not K.is_cuda:
+        return torch.linalg.cholesky(K)
+    L, info = torch.linalg.cholesky_ex(K)
+    _pending_info.append(info)
+    del _pending_info[:-32]
+    return L
+
+
+def check_cholesky():
+    """Raise if a Cholesky factorisation queued since the last check failed (synchronises)."""
+    bad = any(int(i.max()) != 0 for i in _pending_info)
+    _pending_info.clear()
+    if bad:
+        raise torch.linalg.LinAlgError("Cholesky factorisation failed: the covariance matrix is not positive definite")
+
+
 def base_conditional(Kmn, Kmm, Knn, f, *, full_cov=False, q_sqrt=None, white=False):
     """gpflow/conditionals.py base_conditional (1.5.1), called at models.py:66.  f (Z, R); q_sqrt (R, Z, Z) or (Z, R)."""
     R = f.shape[1]
-    Lm = torch.linalg.cholesky(Kmm)
+    Lm = _cholesky(Kmm)
     A = torch.linalg.solve_triangular(Lm, Kmn, upper=False)
     if full_cov:
         fvar = (Knn - A.transpose(0, 1) @ A)[None].expand(R, -1, -1)
@@ -51,7 +74,7 @@ def gauss_kl(q_mu, q_sqrt, K=None):
     if white:
         alpha = q_mu
     else:
-        Lp = torch.linalg.cholesky(K)
+        Lp = _cholesky(K)
         alpha = torch.linalg.solve_triangular(Lp, q_mu, upper=False)
     if q_sqrt.dim() == 2:
         Lq_diag = q_sqrt
@@ -280,6 +303,7 @@ class SVGP:
             loss.backward()
             opt.step()
             history.append(-float(loss.item()))
+            check_cholesky()
             if callback is not None:
                 callback(it, history[-1])
         self.kern.sync_trainable()
@@ -304,7 +328,11 @@ class SVGP:
         return torch.sum(var_exp) * scale - KL
 
     def compute_log_likelihood(self, X=None, Y=None):
-        return float(self._build_likelihood(X, Y).item())
+        v = float(self._build_likelihood(X, Y).item())
+        check_cholesky()
+        return v
 
     def predict_f(self, X_new, full_cov=False):
-        return self._build_predict(X_new, full_cov=full_cov)
+        out = self._build_predict(X_new, full_cov=full_cov)
+        check_cholesky()
+        return out

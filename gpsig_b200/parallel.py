@@ -221,14 +221,9 @@ def sharded_elbo(model, X=None, Y=None, group=None):
     Y = model.Y if Y is None else Y
     n = X.shape[0]
     b, e = column_shards(n, ws)[rk]
-    if model.whiten:
-        f_mean, f_var = model._build_predict(X[b:e])
-        Kzz = None
-    else:
-        f_mean, f_var, Kzz = model._build_predict(X[b:e], return_Kzz=True)
+    f_mean, f_var, Kzz, q_mu, q_sqrt = model._build_predict(X[b:e], return_Kzz=not model.whiten, return_q=True)
     dev = f_mean.device
-    q_sqrt = model._dev(model.q_sqrt, dev)
-    KL = _models.gauss_kl(model._dev(model.q_mu, dev), torch.tril(q_sqrt) if q_sqrt.dim() == 3 else q_sqrt, K=Kzz)
+    KL = _models.gauss_kl(q_mu, q_sqrt, K=Kzz)
     part = torch.sum(model.likelihood.variational_expectations(f_mean, f_var, model._dev(Y[b:e], dev))).reshape(1).double()
     if ws > 1:
         if dist.get_backend(group) == "nccl":
