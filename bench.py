@@ -39,6 +39,7 @@ Nothing here reads /root/reference.  oracle/ is executed only as the CPU baselin
 after the timed region, as the checker.
 """
 import argparse
+import datetime
 import ctypes
 import json
 import os
@@ -223,11 +224,21 @@ def run_reference(args, wl):
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """`nvidia-smi -lms 100` next to the run.  It is started BEFORE the warm-up steps -- its start-up (NVML initialisation,
+    device enumeration) holds driver locks for a few hundred milliseconds and would otherwise stretch the first timed
+    steps -- and only the samples stamped inside [mark_begin(), mark_end()] (the timed region) are reported."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,timestamp")
+
+    def mark_begin(self):
+        self.t0 = datetime.datetime.now()
+
+    def mark_end(self):
+        self.t1 = datetime.datetime.now()
 
     def __init__(self, uuid):
         self.proc = None
+        self.t0 = self.t1 = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", uuid, "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -244,26 +255,43 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
             out = ""
-        sm, smax, pw, reasons = [], [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for ln in out.strip().splitlines():
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); smax.append(float(f[1])); pw.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        if not sm:
+
+        def collect(windowed):
+            sm, smax, pw, reasons = [], [], [], set()
+            for ln in out.strip().splitlines():
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 7:
+                    continue
+                if windowed:
+                    try:
+                        ts = datetime.datetime.strptime(f[7], "%Y/%m/%d %H:%M:%S.%f")
+                    except (ValueError, IndexError):
+                        return None
+                    if ts < self.t0 or ts > self.t1 + datetime.timedelta(milliseconds=100):
+                        continue
+                try:
+                    sm.append(float(f[0])); smax.append(float(f[1])); pw.append(float(f[2]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            return (sm, smax, pw, reasons) if sm else None
+
+        got, window = None, "timed region"
+        if self.t0 is not None and self.t1 is not None:
+            got = collect(True)
+        if got is None:  # timed region shorter than the sampling period (or no timestamps): every sample of the run
+            got, window = collect(False), "warm-up + timed region (timed region shorter than the 100 ms sampling period)"
+        if got is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm, smax, pw, reasons = got
         # "under load": samples drawing more than half of the peak power seen
         lim = 0.5 * max(pw)
         load = [s for s, p in zip(sm, pw) if p >= lim] or sm
         return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(smax), "power_w_max": max(pw), "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "window": window, "reasons": sorted(reasons)}
 
 
 def load_peaks():
@@ -438,16 +466,20 @@ def run_ours(args, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, sampler_uuid=None):
+    def timed(fn, steps, sampler=None):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         barrier()
-        sampler = ClockSampler(sampler_uuid) if sampler_uuid else None
+        if sampler:
+            sampler.mark_begin()
         for e0, e1 in ev:
             flush.zero_()          # L2 flush, outside the event pair
             e0.record()
             fn()
             e1.record()
         barrier()
+        if sampler:
+            torch.cuda.synchronize()
+            sampler.mark_end()
         clocks = sampler.stop() if sampler else None
         ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -455,6 +487,8 @@ def run_ours(args, wl):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), clocks
 
+    uuid = "GPU-" + str(torch.cuda.get_device_properties(dev).uuid).replace("GPU-", "") if rank == 0 else None
+    sampler = ClockSampler(uuid) if uuid else None
     for _ in range(args.warmup):
         step_dev()
     barrier()
@@ -462,8 +496,7 @@ def run_ours(args, wl):
     lib.gpsig_profile_reset()
     lib.gpsig_profile_enable(1)
     l0 = lib.gpsig_launch_count()
-    uuid = "GPU-" + str(torch.cuda.get_device_properties(dev).uuid).replace("GPU-", "") if rank == 0 else None
-    ms_total, clocks = timed(step_dev, args.steps, uuid)
+    ms_total, clocks = timed(step_dev, args.steps, sampler)
     l1 = lib.gpsig_launch_count()
     lib.gpsig_profile_enable(0)
     prof = read_profile(lib, _lib, PROF_CLASSES)

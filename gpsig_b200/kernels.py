@@ -27,6 +27,22 @@ def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
+
+_CONST_CACHE = {}
+
+
+def _dev_const(arr, dev):
+    """Small read-only parameter vectors (lengthscale multipliers, level weights) on the device, cached by VALUE: a fresh
+    pageable host-to-device copy per call is a driver round trip on the critical path of every step."""
+    key = (str(dev), arr.dtype.str, arr.shape, arr.tobytes())
+    t = _CONST_CACHE.get(key)
+    if t is None:
+        if len(_CONST_CACHE) > 256:
+            _CONST_CACHE.clear()
+        t = torch.as_tensor(arr).to(dev)
+        _CONST_CACHE[key] = t
+    return t
+
 class SignatureKernel:
     """Base class (kernels.py:15).  Subclasses set `_kind` and static-kernel parameters."""
 
@@ -150,7 +166,7 @@ class SignatureKernel:
         inv = np.ones(self.num_features) if self.lengthscales is None else 1.0 / np.asarray(self.lengthscales, dtype=np.float64)
         if self.num_lags > 0:
             inv = (np.asarray(self.gamma, dtype=np.float64)[:, None] * inv[None, :]).reshape(-1)
-        return torch.as_tensor(inv.astype(np.float32)).to(dev)
+        return _dev_const(inv.astype(np.float32), dev)
 
     # ---- trainable parameters (the reference: gpflow Parameters with transforms.positive, kernels.py:65-66, :86) ----
     _POSITIVE = ("variances", "sigma", "lengthscales")
@@ -239,7 +255,7 @@ class SignatureKernel:
 
     def _weights(self, dev):
         w = float(self.sigma) * np.asarray(self.variances, dtype=np.float64)                    # kernels.py:471
-        return torch.as_tensor(w.astype(np.float32)).to(dev)
+        return _dev_const(w.astype(np.float32), dev)
 
     def _static_params(self):
         return None
@@ -258,6 +274,9 @@ class SignatureKernel:
 
     def _workspace(self, dev, n1, L1, n2, L2, d):
         lib = _lib.load()
+        need = lib.gpsig_seq_kern_workspace_bytes(n1, L1, n2, L2, d, int(settings.workspace_budget_bytes))
+        if self._ws is not None and self._ws.device == dev and self._ws.numel() >= need:
+            return self._ws        # steady state: no driver query on the step's critical path
         free, _ = torch.cuda.mem_get_info(dev)
         budget = int(min(settings.workspace_budget_bytes, max(free // 2, 64 << 20)))
         need = lib.gpsig_seq_kern_workspace_bytes(n1, L1, n2, L2, d, budget)
