@@ -226,7 +226,9 @@ tens_seq_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
                 };
                 int loaded = 0;
                 for (; loaded < ntile && loaded < S - 1; ++loaded) issue_load();
-                if (ntile > 0) mbar_wait(a_full, item_no & 1u);
+                // EVERY producer waits for the item's A tiles, also one without tiles of its own: the wait is what keeps it
+                // from running an item ahead of producer 0 (where the parity of the A barrier would alias the item before)
+                mbar_wait(a_full, item_no & 1u);
                 for (int q = 0; q < ntile; ++q) {
                     if (loaded < ntile) { issue_load(); ++loaded; }
                     const uint32_t buf = cnt & 1u;

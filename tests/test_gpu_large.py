@@ -265,3 +265,28 @@ def test_diag_pass_of_many_short_sequences_on_a_fresh_kernel():
         k2, _ = _pair(kind, L, d, M)
         Z = 0.5 * np.random.default_rng(1).standard_normal((M * (M + 1) // 2, 3, 2, d))
         assert k2.K_tens_vs_seq(Z, X, increments=True).shape == (3, n)
+
+
+def test_tcgen05_kuf_many_items_per_cta_and_a_single_sequence_chunk():
+    """The tcgen05 Kuf kernel is persistent: with 8 row tiles x 21 sequence chunks (168 items > 148 SMs) some CTAs take two
+    items, and the last chunk holds ONE sequence, so the second warp set's producer has no tiles in it -- it must still
+    stay in step with the producer that loads the A tiles (it used to skip that wait and could run an item ahead)."""
+    from gpsig_b200 import _lib
+    rng = np.random.default_rng(11)
+    L, d, M, nz, n = 64, 8, 5, 64, 161
+    X = random_walks(n, L, d, 9).reshape(n, -1)
+    T = M * (M + 1) // 2
+    Xr = X.reshape(n, L, d)
+    seq, t = rng.integers(0, n, size=(T, nz)), rng.integers(0, L - 1, size=(T, nz))
+    Z = np.stack([Xr[seq, t], Xr[seq, t + 1]], axis=2) + 0.3 * rng.standard_normal((T, nz, 2, d))
+    k, ko = _pair("rbf", L, d, M, lengthscales=float(np.sqrt(d)))
+    got = k.K_tens_vs_seq(Z, X, increments=True, return_levels=True).cpu().numpy()
+    _lib.set_knob("tens_tc", 0)
+    try:
+        cuda_core = k.K_tens_vs_seq(Z, X, increments=True, return_levels=True).cpu().numpy()
+    finally:
+        _lib.set_knob("tens_tc", 1)
+    assert_levels_close(got, cuda_core, msg="tcgen05 vs CUDA-core Kuf")
+    cols = np.r_[0:4, 80:84, 157:161]      # first chunk, a chunk some CTA takes as its second item, the one-sequence chunk
+    ref = ko.K_tens_vs_seq(Z[:, :6], X[cols], increments=True, return_levels=True)
+    assert_levels_close(got[:, :6][:, :, cols], ref, msg="tcgen05 Kuf vs oracle")
