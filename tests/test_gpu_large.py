@@ -290,3 +290,18 @@ def test_tcgen05_kuf_many_items_per_cta_and_a_single_sequence_chunk():
     cols = np.r_[0:4, 80:84, 157:161]      # first chunk, a chunk some CTA takes as its second item, the one-sequence chunk
     ref = ko.K_tens_vs_seq(Z[:, :6], X[cols], increments=True, return_levels=True)
     assert_levels_close(got[:, :6][:, :, cols], ref, msg="tcgen05 Kuf vs oracle")
+
+
+@pytest.mark.parametrize("L,d,M,nz,n", [(2, 3, 2, 1, 1), (3, 8, 5, 2, 3), (17, 9, 4, 5, 7), (65, 10, 6, 3, 2), (130, 12, 3, 9, 5)])
+def test_tcgen05_kuf_edge_shapes(L, d, M, nz, n):
+    """Shortest sequences (one or two time steps of increments), one tensor / one sequence, a single block in the last
+    tile (L = 65, 130), and the three operand layouts (d <= 8; d = 9, 10; d = 12) of the tcgen05 Kuf kernel."""
+    rng = np.random.default_rng(L * 31 + d)
+    X = random_walks(n, L, d, 3).reshape(n, -1)
+    T = M * (M + 1) // 2
+    Xr = X.reshape(n, L, d)
+    seq, t = rng.integers(0, n, size=(T, nz)), rng.integers(0, L - 1, size=(T, nz))
+    Z = np.stack([Xr[seq, t], Xr[seq, t + 1]], axis=2) + 0.2 * rng.standard_normal((T, nz, 2, d))
+    k, ko = _pair("rbf", L, d, M, lengthscales=float(np.sqrt(d)), normalization=False)
+    got = k.K_tens_vs_seq(Z, X, increments=True, return_levels=True).cpu().numpy()
+    assert_levels_close(got, ko.K_tens_vs_seq(Z, X, increments=True, return_levels=True), msg="Kuf edge L=%d d=%d" % (L, d))
