@@ -9,16 +9,17 @@ them -- scaling by lengthscales, the static-kernel Gram (evaluated in float64, s
 differencing of signature_algs.py:26 / :114 / kernels.py:330, normalisation and level weights -- is ordinary tensor
 algebra that torch differentiates (dense contractions on cuBLAS).
 
-This route materialises the Gram of the call (like the reference does), so it is meant for training-sized batches
-(minibatches, diagonal tiles, Z x N inducing blocks); the fused forward kernels stay the path for everything that does not
-need a gradient.  First order only (order == 1), exact mode only (no low-rank).
+This route materialises the INCREMENT tensor of the call in float32 (the reference materialises the float64 Gram and every
+R_m), so it is meant for training-sized batches (minibatches, diagonal tiles, Z x N inducing blocks); when the float64 Gram
+of a call is larger than settings.autodiff_gram_budget_bytes it is evaluated in blocks under activation checkpointing.
+The fused forward kernels stay the path for everything that does not need a gradient.  First order only (order == 1), exact mode only (no low-rank).
 """
 import math
 
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, settings
 
 
 def _stream():
@@ -188,6 +189,17 @@ def add_lags(kern, X):
     return torch.cat((Xd[:, :, None, :], Xq), dim=2).reshape(n, L, -1)
 
 
+def _maybe_checkpoint(fn, *tensors):
+    """Run fn(*tensors) so that autograd keeps only its INPUTS: the float64 Gram of a block and the three or four
+    same-sized intermediates torch would save for its backward (squared distances, the clamp's input, the exponential's
+    output, the differences) are recomputed when the backward pass reaches the block instead of staying resident --
+    the Gram blocks are what limits the batch size of a training step, not their arithmetic."""
+    if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
+        from torch.utils.checkpoint import checkpoint
+        return checkpoint(fn, *tensors, use_reentrant=False)
+    return fn(*tensors)
+
+
 def K_seq_levels(kern, X, X2=None, rows_per_chunk=None):
     """kernels.py:208-237 on RAW sequences (n, L, d); returns (M + 1, n1, n2)."""
     Xs = scale(kern, X)
@@ -195,13 +207,22 @@ def K_seq_levels(kern, X, X2=None, rows_per_chunk=None):
     n1, L1, d = Xs.shape
     n2, L2 = X2s.shape[0], X2s.shape[1]
     flat2 = X2s.reshape(n2 * L2, d)
+    big = 8 * n1 * L1 * n2 * L2 > settings.autodiff_gram_budget_bytes                               # float64 Gram of the call
     if rows_per_chunk is None:
-        rows_per_chunk = max(1, int((1 << 28) // max(1, L1 * n2 * L2)))                             # <= 2 GB of float64 Gram
+        rows_per_chunk = max(1, int((1 << 27) // max(1, L1 * n2 * L2))) if big else n1              # blocks of <= 1 GB
+    difference = kern.difference
+
+    def block(Xc, flat):                                                                          # float32 increments of a row block
+        M = base_gram(kern, Xc.reshape(Xc.shape[0] * L1, d), flat).reshape(Xc.shape[0], L1, n2, L2)
+        if difference:                                                                             # signature_algs.py:26
+            M = M[:, 1:, :, 1:] + M[:, :-1, :, :-1] - M[:, :-1, :, 1:] - M[:, 1:, :, :-1]
+        return M.to(torch.float32)
+
     outs = []
     for c0 in range(0, n1, rows_per_chunk):
         c1 = min(n1, c0 + rows_per_chunk)
-        M = base_gram(kern, Xs[c0:c1].reshape((c1 - c0) * L1, d), flat2).reshape(c1 - c0, L1, n2, L2)
-        outs.append(sigkern_first_order(M, kern.num_levels, kern.difference))
+        M = _maybe_checkpoint(block, Xs[c0:c1], flat2) if big else block(Xs[c0:c1], flat2)
+        outs.append(sigkern_first_order(M, kern.num_levels, difference=False))
     return torch.cat(outs, dim=1)
 
 
@@ -229,13 +250,29 @@ def K_tens_vs_seq_levels(kern, Z, X, increments=False):
     Zs, Xs = scale(kern, Z, tensors=True), scale(kern, X)
     T, nz, d = Zs.shape[0], Zs.shape[1], Zs.shape[-1]
     n, L = Xs.shape[0], Xs.shape[1]
-    flat = Xs.reshape(n * L, d)
-    if increments:
-        M = base_gram(kern, Zs.reshape(T * nz * 2, d), flat).reshape(T, nz, 2, n, L)
-        M = M[:, :, 1] - M[:, :, 0]                                                                # kernels.py:330
+    Zflat = Zs.reshape(-1, d)
+    difference = kern.difference
+
+    def block(Zf, Xc):                                                                            # float32 increments of a block of sequences
+        nc = Xc.shape[0]
+        M = base_gram(kern, Zf, Xc.reshape(nc * L, d))
+        if increments:
+            M = M.reshape(T, nz, 2, nc, L)
+            M = M[:, :, 1] - M[:, :, 0]                                                            # kernels.py:330
+        else:
+            M = M.reshape(T, nz, nc, L)
+        if difference:                                                                             # signature_algs.py:114
+            M = M[..., 1:] - M[..., :-1]
+        return M.to(torch.float32)
+
+    per_seq = max(1, Zflat.shape[0] * L)                                                           # float64 Gram entries per sequence
+    if 8 * per_seq * n > settings.autodiff_gram_budget_bytes:                                      # blocks of <= 512 MB, recomputed in backward
+        chunk = max(1, int((1 << 26) // per_seq))
+        parts = [_maybe_checkpoint(block, Zflat, Xs[c0:min(n, c0 + chunk)]) for c0 in range(0, n, chunk)]
+        M = parts[0] if len(parts) == 1 else torch.cat(parts, dim=2)
     else:
-        M = base_gram(kern, Zs.reshape(T * nz, d), flat).reshape(T, nz, n, L)
-    return tens_vs_seq_first_order(M, kern.num_levels, kern.difference)
+        M = block(Zflat, Xs)
+    return tens_vs_seq_first_order(M, kern.num_levels, difference=False)
 
 
 def finish(kern, levels, diag1=None, diag2=None, symmetric=False, normalize=True, return_levels=False, unit_weights=False):

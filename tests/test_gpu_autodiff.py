@@ -204,3 +204,30 @@ def test_multiclass_and_mean_function_train():
     assert hist[-1] > hist[0]
     probs = m.likelihood.predict_mean(*m.predict_f(X)).detach().cpu().numpy()
     assert probs.shape == (n, C) and np.allclose(probs.sum(1), 1.0, atol=2e-2)
+
+
+def test_blockwise_checkpointed_gram_gives_the_same_values_and_gradients():
+    """settings.autodiff_gram_budget_bytes = 0 forces the blockwise, activation-checkpointed evaluation of the Gram on both
+    differentiable routes (K and K_tens_n_seq_covs): values and gradients must agree with the resident evaluation."""
+    from gpsig_b200 import settings
+    L, d, M = 20, 3, 3
+    results = []
+    old = settings.autodiff_gram_budget_bytes
+    try:
+        for budget in (old, 0):
+            settings.autodiff_gram_budget_bytes = budget
+            k, X, Z, ls, var, rng = _setup("rbf", L, d, M, n=9, nz=5)
+            k.set_trainable(("variances", "lengthscales"))
+            Zt = torch.tensor(Z, device="cuda", dtype=torch.float64, requires_grad=True)
+            Xt = torch.tensor(X, device="cuda", dtype=torch.float64, requires_grad=True)
+            Kzz, Kzx, Kxx = k.K_tens_n_seq_covs(Zt, Xt, increments=True)
+            Kxx_full = k.K(Xt)
+            w = torch.linspace(-1.0, 1.0, Kzx.numel(), device="cuda", dtype=Kzx.dtype).reshape(Kzx.shape)
+            loss = (w * Kzx).sum() + Kzz.sum() + (Kxx * Kxx).sum() + (Kxx_full * Kxx_full).sum()
+            loss.backward()
+            results.append([loss.detach().cpu().numpy(), Zt.grad.cpu().numpy(), Xt.grad.cpu().numpy(),
+                            k._raw["lengthscales"].grad.cpu().numpy(), k._raw["variances"].grad.cpu().numpy()])
+    finally:
+        settings.autodiff_gram_budget_bytes = old
+    for a, b, name in zip(results[0], results[1], ("loss", "dZ", "dX", "dlengthscales", "dvariances")):
+        assert_close(b, a, tol=1e-5, msg=name)
