@@ -65,6 +65,17 @@ def test_first_order_4d_vs_oracle(n1, L1, n2, L2, nlev, diff):
     assert_levels_close(got, ref, msg="fo4d")
 
 
+def test_first_order_many_items_per_warp():
+    """enough pairs that every warp streams several items back to back (ring wrap-around, box refills across items)"""
+    from gpsig_b200 import signature_algs as S
+    n1, L1, n2, L2, nlev = 40, 64, 300, 64, 5
+    M = _gram(n1, L1, n2, L2, 3, seed=7)
+    got = S.signature_kern_first_order(_dev(M), nlev, difference=True).cpu().numpy()
+    rows, cols = np.r_[0:2, 38:40], np.r_[0:3, 297:300]
+    ref = O.signature_kern_first_order(M[rows][:, :, cols], nlev, difference=True)
+    assert_levels_close(got[:, rows][:, :, cols], ref, msg="many items per warp")
+
+
 @pytest.mark.parametrize("n,L,nlev,diff", [(6, 64, 4, True), (9, 128, 5, True), (5, 13, 3, True), (4, 32, 4, False)])
 def test_first_order_3d_vs_oracle(n, L, nlev, diff):
     from gpsig_b200 import signature_algs as S
